@@ -1,0 +1,390 @@
+// kernels_simt.cuh -- CUDA-core kernels of the RNN-T loss hot path (sm_100a).
+//
+//   lse_gather_kernel   log-softmax denominators + (blank, label) log-prob gather, one pass
+//                       (replaces reduce_max + reduce_exp + logp(): gpu_rnnt.h:73-80,
+//                        reduce.h:45-104, gpu_rnnt_kernel.h:5-9)
+//   alpha_beta_kernel   forward/backward lattice recurrences as anti-diagonal wavefronts over a
+//                       DIAGONAL-MAJOR cache of the two log-probs per cell
+//                       (replaces gpu_rnnt_kernel.h:11-47, 79-113; arithmetic of cpu_rnnt.h:175-253)
+//   rnnt_grad_kernel    gradient w.r.t. logits (gpu_rnnt_kernel.h:143-179), padded cells zeroed
+//                       in the same pass (replaces the cudaMemsetAsync of gpu_rnnt.h:109)
+//   cell_coef_kernel    per-cell coefficients consumed by the fused joint backward epilogue
+//   zgen/sgemm/...      fp32 building blocks of the exact (RNNTB200_FP32_EXACT) joint path
+//
+// Data layout ("skewed" planes): a per-utterance plane stores cell (t,u) at row n=t+u, column u:
+//     sk(b,t,u) = b*SK + (t+u)*maxU + u,   SK = (maxT+maxU-1)*maxU
+// so that step n of a wavefront touches ONE contiguous row (coalesced), which the reference's
+// (t*maxU+u) planes cannot offer (stride maxU-1 between neighbouring threads).
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+namespace rb {
+
+template <typename T> __device__ __forceinline__ T neg_inf();
+template <> __device__ __forceinline__ float neg_inf<float>() { return -CUDART_INF_F; }
+template <> __device__ __forceinline__ double neg_inf<double>() { return -CUDART_INF; }
+
+__device__ __forceinline__ float  xexp(float x)    { return expf(x); }
+__device__ __forceinline__ double xexp(double x)   { return exp(x); }
+__device__ __forceinline__ float  xlog(float x)    { return logf(x); }
+__device__ __forceinline__ double xlog(double x)   { return log(x); }
+__device__ __forceinline__ float  xlog1p(float x)  { return log1pf(x); }
+__device__ __forceinline__ double xlog1p(double x) { return log1p(x); }
+
+// rnnt_helper::log_sum_exp -- rnnt_helper.h:16-24 (including the -inf short circuits)
+template <typename T>
+__device__ __forceinline__ T log_sum_exp(T a, T b) {
+    if (a == neg_inf<T>()) return b;
+    if (b == neg_inf<T>()) return a;
+    return a > b ? xlog1p(xexp(b - a)) + a : xlog1p(xexp(a - b)) + b;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_max(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { T w = __shfl_xor_sync(0xffffffffu, v, o); v = w > v ? w : v; }
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct CellIdx { int b, t, u; };
+__device__ __forceinline__ CellIdx decode_cell(long long cell, int maxT, int maxU) {
+    CellIdx c;
+    c.u = (int)(cell % maxU);
+    long long bt = cell / maxU;
+    c.t = (int)(bt % maxT);
+    c.b = (int)(bt / maxT);
+    return c;
+}
+__device__ __forceinline__ long long sk_index(int b, int t, int u, int maxU, long long SK) {
+    return (long long)b * SK + (long long)(t + u) * maxU + u;
+}
+
+// ---------------------------------------------------------------------------------------------
+// lse + gather: one warp per lattice cell (row of V logits).  Row r of `logits` is natural cell
+// row0 + r.  Two in-cache passes (max, then sum exp(x-max)) reproduce the reference's
+// reduce_max / reduce_exp arithmetic; the row (<= 16 KB) is served by L1 on the second pass.
+// Writes lse[cell] (natural order) and lp_blank / lp_label at the skewed index.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) lse_gather_kernel(const T* __restrict__ logits, long long row0,
+                                                         long long nrows, int V, const int* __restrict__ xlen,
+                                                         const int* __restrict__ ylen,
+                                                         const int* __restrict__ labels, int maxT, int maxU,
+                                                         long long SK, int blank, T* __restrict__ lse,
+                                                         T* __restrict__ lpb, T* __restrict__ lpl) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const long long cell = row0 + row;
+    const CellIdx c = decode_cell(cell, maxT, maxU);
+    const int Tn = xlen[c.b], Un = ylen[c.b] + 1;
+    if (c.t >= Tn || c.u >= Un) return;  // padded cell: never read downstream
+    const T* x = logits + row * (long long)V;
+    T m = neg_inf<T>();
+    for (int v = lane; v < V; v += 32) { T xv = x[v]; m = xv > m ? xv : m; }
+    m = warp_max(m);
+    T s = 0;
+    for (int v = lane; v < V; v += 32) s += xexp(x[v] - m);
+    s = warp_sum(s);
+    if (lane == 0) {
+        const T l = m + xlog(s);
+        lse[cell] = l;
+        const long long k = sk_index(c.b, c.t, c.u, maxU, SK);
+        lpb[k] = x[blank] - l;
+        if (c.u < Un - 1) lpl[k] = x[labels[(long long)c.b * (maxU - 1) + c.u]] - l;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// alpha / beta wavefronts.  grid = (B, 2): blockIdx.y == 0 runs alpha, 1 runs beta, so the two
+// recurrences of one utterance overlap on different SMs.  Thread u owns lattice column u and
+// walks the anti-diagonals n = t+u; its own previous value stays in a register, the neighbour's
+// arrives by warp shuffle (and through a 2-slot shared-memory mailbox across warp boundaries,
+// one __syncthreads per step only when maxU > 32).  The two cached log-probs of the thread's OWN
+// cell are the only global reads: row n of the skewed planes, fully coalesced, software-prefetched
+// PF rows ahead because they do not depend on the recurrence.
+//   alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1))        cpu_rnnt.h:182-195
+//   beta(t,u)  = LSE(beta(t+1,u)+lpb(t,u),    beta(t,u+1)+lpl(t,u))            cpu_rnnt.h:223-236
+//   llForward  = alpha(T-1,U-1)+lpb(T-1,U-1); llBackward = beta(0,0)           cpu_rnnt.h:209,251
+// ---------------------------------------------------------------------------------------------
+template <typename T, int PF>
+__global__ void __launch_bounds__(1024) alpha_beta_kernel(const T* __restrict__ lpb, const T* __restrict__ lpl,
+                                                          T* __restrict__ alphas, T* __restrict__ betas,
+                                                          T* __restrict__ llf, T* __restrict__ llb,
+                                                          const int* __restrict__ xlen,
+                                                          const int* __restrict__ ylen, int maxU, long long SK) {
+    const int b = blockIdx.x;
+    const bool is_beta = blockIdx.y == 1;
+    const int u = threadIdx.x, lane = u & 31, warp = u >> 5;
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    const int nsteps = Tn + Un - 1;
+    const bool multi = blockDim.x > 32;
+    const bool col_ok = u < Un;
+    __shared__ T mailbox[2][32];
+
+    const T* pb = lpb + (long long)b * SK + u;
+    const T* pl = lpl + (long long)b * SK + u;
+    T* po = (is_beta ? betas : alphas) + (long long)b * SK + u;
+
+    T own = neg_inf<T>();   // alpha: alpha(t-1,u)+lpb(t-1,u)   beta: beta(t+1,u)
+    T pass = neg_inf<T>();  // alpha: alpha(t,u)+lpl(t,u)       beta: beta(t,u)   (handed to the neighbour)
+    T result = 0;
+
+    T cb[PF], cl[PF], nb[PF], nl[PF];
+    auto row_of = [&](int i) { return is_beta ? nsteps - 1 - i : i; };  // i-th step -> diagonal
+    auto fetch = [&](int i0, T* vb, T* vl) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int i = i0 + j;
+            const bool ok = col_ok && i < nsteps;
+            const long long off = (long long)row_of(ok ? i : 0) * maxU;
+            vb[j] = ok ? pb[off] : T(0);
+            vl[j] = ok ? pl[off] : T(0);
+        }
+    };
+    fetch(0, nb, nl);
+    for (int i0 = 0; i0 < nsteps; i0 += PF) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+        fetch(i0 + PF, nb, nl);
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int i = i0 + j;
+            if (i < nsteps) {  // uniform across the block
+                const int n = row_of(i);
+                const int t = n - u;
+                T nbr = is_beta ? __shfl_down_sync(0xffffffffu, pass, 1) : __shfl_up_sync(0xffffffffu, pass, 1);
+                if (!is_beta && lane == 0) nbr = (warp > 0) ? mailbox[(i & 1) ^ 1][warp - 1] : neg_inf<T>();
+                if (is_beta && lane == 31) nbr = (multi && warp + 1 < (int)(blockDim.x >> 5))
+                                                     ? mailbox[(i & 1) ^ 1][warp + 1] : neg_inf<T>();
+                const bool active = col_ok && t >= 0 && t < Tn;
+                if (active) {
+                    const T vb = cb[j], vl = cl[j];
+                    if (!is_beta) {
+                        // alpha(t,u); own == -inf when t == 0, nbr is unused (forced -inf) when u == 0
+                        const T emit = (u > 0) ? nbr : neg_inf<T>();
+                        const T a = (n == 0) ? T(0) : log_sum_exp(emit, own);
+                        po[(long long)n * maxU] = a;
+                        own = a + vb;
+                        pass = a + vl;
+                        result = own;  // at the last cell: alpha(T-1,U-1)+lpb(T-1,U-1)
+                    } else {
+                        const T no_emit = (t < Tn - 1) ? own + vb : neg_inf<T>();
+                        const T emit = (u < Un - 1) ? nbr + vl : neg_inf<T>();
+                        const T bt = (t == Tn - 1 && u == Un - 1) ? vb : log_sum_exp(emit, no_emit);
+                        po[(long long)n * maxU] = bt;
+                        own = bt;
+                        pass = bt;
+                        result = bt;
+                    }
+                }
+                if (multi) {
+                    if (!is_beta && lane == 31) mailbox[i & 1][warp] = pass;
+                    if (is_beta && lane == 0) mailbox[i & 1][warp] = pass;
+                    __syncthreads();
+                }
+            }
+        }
+    }
+    if (!is_beta && u == Un - 1) llf[b] = result;
+    if (is_beta && u == 0) llb[b] = result;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gradient w.r.t. logits, one warp per cell row -- gpu_rnnt_kernel.h:143-179:
+//   g[v] = exp(alpha+beta+lp_v-ll) - [v==blank & last cell] exp(alpha+lp_v-ll)
+//          - [v==blank & t<T-1] exp(alpha+lp_v-ll+beta(t+1,u)) - [v==label_u & u<U-1] exp(alpha+lp_v-ll+beta(t,u+1))
+// normalised by llForward (gpu_rnnt.h:198-200).  Padded cells are written 0 here (the reference
+// memsets the whole tensor first, gpu_rnnt.h:109).  `out` may alias `logits` (in-place, used by the
+// exact joint path).  gscale (nullable): per-utterance upstream gradient, pre-multiplied.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) rnnt_grad_kernel(const T* logits, T* out, long long row0, long long nrows,
+                                                        int V, const int* __restrict__ xlen,
+                                                        const int* __restrict__ ylen,
+                                                        const int* __restrict__ labels, int maxT, int maxU,
+                                                        long long SK, int blank, const T* __restrict__ lse,
+                                                        const T* __restrict__ alphas, const T* __restrict__ betas,
+                                                        const T* __restrict__ llf, const T* __restrict__ gscale) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const long long cell = row0 + row;
+    const CellIdx c = decode_cell(cell, maxT, maxU);
+    const int Tn = xlen[c.b], Un = ylen[c.b] + 1;
+    const T* x = logits + row * (long long)V;
+    T* g = out + row * (long long)V;
+    if (c.t >= Tn || c.u >= Un) {
+        for (int v = lane; v < V; v += 32) g[v] = T(0);
+        return;
+    }
+    const long long k = sk_index(c.b, c.t, c.u, maxU, SK);
+    const T a = alphas[k], bt = betas[k], ll = llf[c.b], l = lse[cell];
+    const T gs = gscale ? gscale[c.b] : T(1);
+    const int label = (c.u < Un - 1) ? labels[(long long)c.b * (maxU - 1) + c.u] : -1;
+    T sb = 0, sl = 0;
+    if (c.t == Tn - 1 && c.u == Un - 1) sb = xexp(a + (x[blank] - l) - ll);
+    if (c.t < Tn - 1) sb = xexp(a + (x[blank] - l) - ll + betas[k + maxU]);        // beta(t+1,u): next diagonal, same column
+    if (label >= 0) sl = xexp(a + (x[label] - l) - ll + betas[k + maxU + 1]);      // beta(t,u+1): next diagonal, next column
+    const T kd = a + bt - ll - l;
+    for (int v = lane; v < V; v += 32) {
+        T gr = xexp(x[v] + kd);
+        if (v == blank) gr -= sb;
+        if (v == label) gr -= sl;
+        g[v] = gr * gs;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Per-cell coefficients for the fused (tensor-core) backward epilogue, natural cell order:
+//   coef[cell] = (kd, g, g*sb, g*sl) with dlogit[v] = g*exp(x_v + kd) - [v==blank] g*sb - [v==label] g*sl
+// Invalid (padded) cells get (-inf, 0, 0, 0) so that their rows contribute exactly 0.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) cell_coef_kernel(long long ncells, const int* __restrict__ xlen,
+                                                        const int* __restrict__ ylen, int maxT, int maxU,
+                                                        long long SK, const float* __restrict__ lse,
+                                                        const float* __restrict__ lpb,
+                                                        const float* __restrict__ lpl,
+                                                        const float* __restrict__ alphas,
+                                                        const float* __restrict__ betas,
+                                                        const float* __restrict__ llf,
+                                                        const float* __restrict__ gscale, float4* __restrict__ coef) {
+    const long long cell = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (cell >= ncells) return;
+    const CellIdx c = decode_cell(cell, maxT, maxU);
+    const int Tn = xlen[c.b], Un = ylen[c.b] + 1;
+    float4 o = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
+    if (c.t < Tn && c.u < Un) {
+        const long long k = sk_index(c.b, c.t, c.u, maxU, SK);
+        const float a = alphas[k], bt = betas[k], ll = llf[c.b], g = gscale ? gscale[c.b] : 1.f;
+        float sb = 0.f, sl = 0.f;
+        if (c.t == Tn - 1 && c.u == Un - 1) sb = expf(a + lpb[k] - ll);
+        if (c.t < Tn - 1) sb = expf(a + lpb[k] - ll + betas[k + maxU]);
+        if (c.u < Un - 1) sl = expf(a + lpl[k] - ll + betas[k + maxU + 1]);
+        o = make_float4(a + bt - ll - lse[cell], g, g * sb, g * sl);
+    }
+    coef[cell] = o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fp32 exact joint path building blocks
+// ---------------------------------------------------------------------------------------------
+// z[r,h] = tanh(enc[b,t,h] + pred[b,u,h]) for natural cells row0 .. row0+nrows   (model.py:158-163)
+__global__ void __launch_bounds__(256) zgen_kernel(const float* __restrict__ enc, const float* __restrict__ pred,
+                                                   float* __restrict__ z, long long row0, long long nrows, int maxT,
+                                                   int maxU, int H) {
+    const long long total = nrows * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / H;
+        const int h = (int)(i - r * H);
+        const CellIdx c = decode_cell(row0 + r, maxT, maxU);
+        z[i] = tanhf(enc[((long long)c.b * maxT + c.t) * H + h] + pred[((long long)c.b * maxU + c.u) * H + h]);
+    }
+}
+
+// C[m,n] = (accumulate ? C : 0) + sum_k A(m,k) B(k,n) (+ bias[n]); generic strides so that the three
+// products of the exact path (Z.W, dL.W^T, Z^T.dL) share one kernel.  64x64x16 tiles, 256 threads,
+// 4x4 register micro-tiles; the smem tile loads pick the thread mapping by which stride is unit.
+template <bool A_K_CONTIG, bool B_N_CONTIG>
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                    float* __restrict__ C, const float* __restrict__ bias, int M,
+                                                    int N, int K, long long sAm, long long sAk, long long sBk,
+                                                    long long sBn, long long ldc, int accumulate) {
+    constexpr int BM = 64, BN = 64, BK = 16;
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid & 15, ty = tid >> 4;  // 16 x 16 threads, 4x4 outputs each
+    float acc[4][4] = {};
+    for (int k0 = 0; k0 < K; k0 += BK) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {  // 1024 elements per operand tile, 4 per thread
+            const int e = tid + i * 256;
+            int am, ak;
+            if (A_K_CONTIG) { ak = e & 15; am = e >> 4; } else { am = e & 63; ak = e >> 6; }
+            const int gm = m0 + am, gk = k0 + ak;
+            As[ak][am] = (gm < M && gk < K) ? A[gm * sAm + gk * sAk] : 0.f;
+            int bn, bk;
+            if (B_N_CONTIG) { bn = e & 63; bk = e >> 6; } else { bk = e & 15; bn = e >> 4; }
+            const int gn = n0 + bn, gk2 = k0 + bk;
+            Bs[bk][bn] = (gn < N && gk2 < K) ? Bm[gk2 * sBk + gn * sBn] : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[k][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int gm = m0 + ty * 4 + i;
+        if (gm >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gn = n0 + tx * 4 + j;
+            if (gn >= N) continue;
+            float v = acc[i][j] + (bias ? bias[gn] : 0.f);
+            float* c = C + (long long)gm * ldc + gn;
+            *c = accumulate ? *c + v : v;
+        }
+    }
+}
+
+// dpre = dz * (1 - z^2); d_enc[b,t,:] += sum_u dpre, d_pred[b,u,:] += sum_t dpre (atomics; exact path only)
+__global__ void __launch_bounds__(256) dz_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z,
+                                                        long long row0, long long nrows, int maxT, int maxU, int H,
+                                                        float* __restrict__ d_enc, float* __restrict__ d_pred) {
+    const long long total = nrows * H;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / H;
+        const int h = (int)(i - r * H);
+        const CellIdx c = decode_cell(row0 + r, maxT, maxU);
+        const float zz = z[i];
+        const float g = dz[i] * (1.f - zz * zz);
+        if (g != 0.f) {
+            atomicAdd(d_enc + ((long long)c.b * maxT + c.t) * H + h, g);
+            atomicAdd(d_pred + ((long long)c.b * maxU + c.u) * H + h, g);
+        }
+    }
+}
+
+// out[v] += sum_r x[r,v]   (db of the exact path)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, long long nrows, int V,
+                                                     float* __restrict__ out) {
+    const int v = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int ry = threadIdx.x >> 5;  // 8 row lanes
+    float s = 0.f;
+    if (v < V)
+        for (long long r = blockIdx.y * 8 + ry; r < nrows; r += (long long)gridDim.y * 8) s += x[r * V + v];
+    __shared__ float sm[8][33];
+    sm[ry][threadIdx.x & 31] = s;
+    __syncthreads();
+    if (ry == 0 && v < V) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sm[i][threadIdx.x & 31];
+        atomicAdd(out + v, t);
+    }
+}
+
+}  // namespace rb

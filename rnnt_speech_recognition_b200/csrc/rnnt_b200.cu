@@ -1,0 +1,397 @@
+// rnnt_b200.cu -- C ABI (include/rnnt_b200.h) and host-side orchestration of the RNN-T loss hot
+// path on B200.  No allocation, no host synchronisation (except the reference-mandated one in
+// compute_rnnt_loss), everything stream-ordered on the caller's stream.
+#include "../../include/rnnt_b200.h"
+
+#include <atomic>
+#include <cstdio>
+#include <cstdint>
+
+#include <cuda_runtime.h>
+
+#include "kernels_simt.cuh"
+#ifndef RNNTB200_NO_TC
+#include "joint_tc.cuh"
+#endif
+
+namespace {
+
+std::atomic<unsigned long long> g_launches{0};
+#define RB_LAUNCHED(n) g_launches.fetch_add((n), std::memory_order_relaxed)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+inline long long skew_plane(int maxT, int maxU) { return (long long)(maxT + maxU - 1) * maxU; }
+
+// Workspace of the loss op proper (shared by compute_rnnt_loss and the joint path).
+template <typename T>
+struct LossWs {
+    T *lpb, *lpl, *alphas, *betas, *lse, *llf, *llb;
+    size_t bytes;
+    LossWs(void* base, int B, int maxT, int maxU) {
+        const size_t SK = (size_t)skew_plane(maxT, maxU), N = (size_t)maxT * maxU;
+        T* p = reinterpret_cast<T*>(base);
+        lpb = p; p += B * SK;
+        lpl = p; p += B * SK;
+        alphas = p; p += B * SK;
+        betas = p; p += B * SK;
+        lse = p; p += B * N;
+        llf = p; p += B;
+        llb = p; p += B;
+        bytes = (size_t)B * (4 * SK + N + 2) * sizeof(T);
+    }
+};
+
+__global__ void negate_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+__global__ void negate_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = -in[i];
+}
+
+inline rnntStatus_t check_launch() { return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED; }
+
+template <typename T>
+rnntStatus_t launch_alpha_beta(const LossWs<T>& w, const int* xlen, const int* ylen, int B, int maxT, int maxU,
+                               cudaStream_t s) {
+    const int threads = (maxU + 31) / 32 * 32;
+    constexpr int PF = sizeof(T) == 4 ? 8 : 4;
+    rb::alpha_beta_kernel<T, PF><<<dim3(B, 2), threads, 0, s>>>(w.lpb, w.lpl, w.alphas, w.betas, w.llf, w.llb, xlen,
+                                                                ylen, maxU, skew_plane(maxT, maxU));
+    RB_LAUNCHED(1);
+    return check_launch();
+}
+
+// loss op on materialised logits: lse+gather -> alpha/beta -> (grad).  costs stay on device in w.llf.
+template <typename T>
+rnntStatus_t loss_op(const T* acts, T* grads, const int* labels, const int* ylen, const int* xlen, const T* gscale,
+                     int V, int B, int maxT, int maxU, int blank, void* workspace, cudaStream_t s) {
+    if (maxU > 1024) {
+        fprintf(stderr, "rnnt_b200: maxU=%d exceeds the 1024 label positions per utterance limit\n", maxU);
+        return RNNT_STATUS_INVALID_VALUE;
+    }
+    LossWs<T> w(workspace, B, maxT, maxU);
+    const long long N = (long long)B * maxT * maxU, SK = skew_plane(maxT, maxU);
+    const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
+    rb::lse_gather_kernel<T><<<blocks, 256, 0, s>>>(acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK, blank, w.lse,
+                                                    w.lpb, w.lpl);
+    RB_LAUNCHED(1);
+    if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    if (launch_alpha_beta(w, xlen, ylen, B, maxT, maxU, s)) return RNNT_STATUS_EXECUTION_FAILED;
+    if (grads) {
+        rb::rnnt_grad_kernel<T><<<blocks, 256, 0, s>>>(acts, grads, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
+                                                       blank, w.lse, w.alphas, w.betas, w.llf, gscale);
+        RB_LAUNCHED(1);
+        if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+template <typename T>
+rnntStatus_t compute_impl(const T* acts, T* grads, const int* labels, const int* ylen, const int* xlen, int V, int B,
+                          T* costs_host, void* workspace, rnntOptions opt) {
+    // argument checks of rnnt_entrypoint.cpp:49-60
+    if (!acts || !labels || !ylen || !xlen || !costs_host || !workspace || V <= 0 || B <= 0 || opt.maxT <= 0 ||
+        opt.maxU <= 0)
+        return RNNT_STATUS_INVALID_VALUE;
+    if (opt.loc == RNNT_CPU) {
+        fprintf(stderr, "rnnt_b200: RNNT_CPU requested but this library has no CPU path (no fallback by design)\n");
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    if (opt.loc != RNNT_GPU) return RNNT_STATUS_INVALID_VALUE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(opt.stream);
+    rnntStatus_t st = loss_op<T>(acts, grads, labels, ylen, xlen, nullptr, V, B, opt.maxT, opt.maxU, opt.blank_label,
+                                 workspace, s);
+    if (st) return st;
+    // costs to HOST + sync + negate, as gpu_rnnt.h:209-213
+    LossWs<T> w(workspace, B, opt.maxT, opt.maxU);
+    if (cudaMemcpyAsync(costs_host, w.llf, sizeof(T) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return RNNT_STATUS_MEMOPS_FAILED;
+    if (cudaStreamSynchronize(s) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    for (int i = 0; i < B; ++i) costs_host[i] = -costs_host[i];
+    return RNNT_STATUS_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------
+// joint path workspace
+// ------------------------------------------------------------------------------------------
+struct JointWs {
+    LossWs<float> loss;
+    float4* coef;      // (N) per-cell backward coefficients (TC path)
+    char* scratch;     // path-specific
+    size_t scratch_bytes;
+    long long chunk_rows;  // exact path
+    size_t total;
+    JointWs(const rnntb200JointDesc& d, void* base) : loss(base, d.B, d.maxT, d.maxU) {
+        const size_t N = (size_t)d.B * d.maxT * d.maxU;
+        size_t off = align_up(loss.bytes, 256);
+        coef = reinterpret_cast<float4*>(static_cast<char*>(base) + off);
+        off += align_up(N * sizeof(float4), 256);
+        scratch = static_cast<char*>(base) + off;
+        if (d.precision == RNNTB200_FP32_EXACT) {
+            const size_t per_row = (size_t)(2 * d.H + d.V) * sizeof(float);
+            size_t ch = ((size_t)1 << 30) / per_row;
+            if (ch < 256) ch = 256;
+            if (ch > N) ch = N;
+            chunk_rows = (long long)ch;
+            scratch_bytes = ch * per_row;
+        } else {
+#ifndef RNNTB200_NO_TC
+            chunk_rows = 0;
+            scratch_bytes = rb::tc_scratch_bytes(d);
+#else
+            chunk_rows = 0;
+            scratch_bytes = 0;
+#endif
+        }
+        total = off + align_up(scratch_bytes, 256);
+    }
+};
+
+bool desc_ok(const rnntb200JointDesc* d) {
+    return d && d->B > 0 && d->maxT > 0 && d->maxU > 0 && d->H > 0 && d->V > 0 && d->blank_label >= 0 &&
+           d->blank_label < d->V && (d->precision == RNNTB200_FP32_EXACT || d->precision == RNNTB200_BF16_TC) &&
+           d->maxU <= 1024;
+}
+
+inline unsigned ew_blocks(long long total) {
+    long long b = (total + 255) / 256;
+    return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+void launch_sgemm_zw(const float* Z, const float* W, const float* bias, float* L, long long rows, int H, int V,
+                     cudaStream_t s) {
+    dim3 grid((V + 63) / 64, (unsigned)((rows + 63) / 64));
+    rb::sgemm_kernel<true, true><<<grid, 256, 0, s>>>(Z, W, L, bias, (int)rows, V, H, H, 1, V, 1, V, 0);
+    RB_LAUNCHED(1);
+}
+
+rnntStatus_t exact_forward(const rnntb200JointDesc& d, const JointWs& ws, const float* enc, const float* pred,
+                           const float* W, const float* bias, const int* labels, const int* ylen, const int* xlen,
+                           cudaStream_t s) {
+    const long long N = (long long)d.B * d.maxT * d.maxU, SK = skew_plane(d.maxT, d.maxU);
+    float* Z = reinterpret_cast<float*>(ws.scratch);
+    float* L = Z + ws.chunk_rows * d.H;
+    for (long long r0 = 0; r0 < N; r0 += ws.chunk_rows) {
+        const long long rows = (N - r0 < ws.chunk_rows) ? N - r0 : ws.chunk_rows;
+        rb::zgen_kernel<<<ew_blocks(rows * d.H), 256, 0, s>>>(enc, pred, Z, r0, rows, d.maxT, d.maxU, d.H);
+        RB_LAUNCHED(1);
+        launch_sgemm_zw(Z, W, bias, L, rows, d.H, d.V, s);
+        rb::lse_gather_kernel<float><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
+            L, r0, rows, d.V, xlen, ylen, labels, d.maxT, d.maxU, SK, d.blank_label, ws.loss.lse, ws.loss.lpb,
+            ws.loss.lpl);
+        RB_LAUNCHED(1);
+        if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+rnntStatus_t exact_backward(const rnntb200JointDesc& d, const JointWs& ws, const float* enc, const float* pred,
+                            const float* W, const float* bias, const int* labels, const int* ylen, const int* xlen,
+                            const float* grad_costs, float* d_enc, float* d_pred, float* dW, float* db,
+                            cudaStream_t s) {
+    const long long N = (long long)d.B * d.maxT * d.maxU, SK = skew_plane(d.maxT, d.maxU);
+    float* Z = reinterpret_cast<float*>(ws.scratch);
+    float* L = Z + ws.chunk_rows * d.H;
+    float* dZ = L + ws.chunk_rows * d.V;
+    if (cudaMemsetAsync(d_enc, 0, sizeof(float) * (size_t)d.B * d.maxT * d.H, s) != cudaSuccess ||
+        cudaMemsetAsync(d_pred, 0, sizeof(float) * (size_t)d.B * d.maxU * d.H, s) != cudaSuccess ||
+        cudaMemsetAsync(dW, 0, sizeof(float) * (size_t)d.H * d.V, s) != cudaSuccess ||
+        cudaMemsetAsync(db, 0, sizeof(float) * (size_t)d.V, s) != cudaSuccess)
+        return RNNT_STATUS_MEMOPS_FAILED;
+    for (long long r0 = 0; r0 < N; r0 += ws.chunk_rows) {
+        const long long rows = (N - r0 < ws.chunk_rows) ? N - r0 : ws.chunk_rows;
+        rb::zgen_kernel<<<ew_blocks(rows * d.H), 256, 0, s>>>(enc, pred, Z, r0, rows, d.maxT, d.maxU, d.H);
+        launch_sgemm_zw(Z, W, bias, L, rows, d.H, d.V, s);
+        // dlogits in place (gpu_rnnt_kernel.h:143-179 formula, times the upstream per-utterance gradient)
+        rb::rnnt_grad_kernel<float><<<(unsigned)((rows * 32 + 255) / 256), 256, 0, s>>>(
+            L, L, r0, rows, d.V, xlen, ylen, labels, d.maxT, d.maxU, SK, d.blank_label, ws.loss.lse, ws.loss.alphas,
+            ws.loss.betas, ws.loss.llf, grad_costs);
+        // dZ = dL . W^T      (rows x V) . (V x H):  B(k=v, n=h) = W[h*V + v]
+        {
+            dim3 grid((d.H + 63) / 64, (unsigned)((rows + 63) / 64));
+            rb::sgemm_kernel<true, false><<<grid, 256, 0, s>>>(L, W, dZ, nullptr, (int)rows, d.H, d.V, d.V, 1, 1, d.V,
+                                                               d.H, 0);
+        }
+        rb::dz_reduce_kernel<<<ew_blocks(rows * d.H), 256, 0, s>>>(dZ, Z, r0, rows, d.maxT, d.maxU, d.H, d_enc,
+                                                                   d_pred);
+        // dW += Z^T . dL     (H x rows) . (rows x V):  A(m=h, k=r) = Z[r*H + h]
+        {
+            dim3 grid((d.V + 63) / 64, (d.H + 63) / 64);
+            rb::sgemm_kernel<false, true><<<grid, 256, 0, s>>>(Z, L, dW, nullptr, d.H, d.V, (int)rows, 1, d.H, d.V, 1,
+                                                               d.V, 1);
+        }
+        {
+            long long gy = (rows + 255) / 256;
+            if (gy > 512) gy = 512;
+            rb::colsum_kernel<<<dim3((d.V + 31) / 32, (unsigned)gy), 256, 0, s>>>(L, rows, d.V, db);
+        }
+        RB_LAUNCHED(7);
+        if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+int get_warprnnt_version() { return 1; }
+
+const char* rnntGetStatusString(rnntStatus_t status) {
+    switch (status) {
+        case RNNT_STATUS_SUCCESS: return "no error";
+        case RNNT_STATUS_MEMOPS_FAILED: return "cuda memcpy or memset failed";
+        case RNNT_STATUS_INVALID_VALUE: return "invalid value";
+        case RNNT_STATUS_EXECUTION_FAILED: return "execution failed";
+        case RNNT_STATUS_UNKNOWN_ERROR:
+        default: return "unknown error";
+    }
+}
+
+rnntStatus_t get_workspace_size(int maxT, int maxU, int minibatch, bool gpu, size_t* size_bytes, size_t dtype_size) {
+    if (minibatch <= 0 || maxT <= 0 || maxU <= 0 || !size_bytes) return RNNT_STATUS_INVALID_VALUE;
+    if (!gpu) {  // reference CPU figure, rnnt_entrypoint.cpp:109-118 (informational only)
+        *size_bytes = dtype_size * (size_t)maxT * maxU * 4 * (size_t)minibatch;
+        return RNNT_STATUS_SUCCESS;
+    }
+    const size_t SK = (size_t)skew_plane(maxT, maxU);
+    *size_bytes = (size_t)minibatch * (4 * SK + (size_t)maxT * maxU + 2) * dtype_size;
+    return RNNT_STATUS_SUCCESS;
+}
+
+rnntStatus_t compute_rnnt_loss(const float* const activations, float* gradients, const int* const flat_labels,
+                               const int* const label_lengths, const int* const input_lengths, int alphabet_size,
+                               int minibatch, float* costs, void* workspace, rnntOptions options) {
+    return compute_impl<float>(activations, gradients, flat_labels, label_lengths, input_lengths, alphabet_size,
+                               minibatch, costs, workspace, options);
+}
+
+rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gradients,
+                                    const int* const flat_labels, const int* const label_lengths,
+                                    const int* const input_lengths, int alphabet_size, int minibatch,
+                                    double* costs, void* workspace, rnntOptions options) {
+    return compute_impl<double>(activations, gradients, flat_labels, label_lengths, input_lengths, alphabet_size,
+                                minibatch, costs, workspace, options);
+}
+
+rnntStatus_t rnntb200_loss_device(const float* activations, float* gradients, const int* flat_labels,
+                                  const int* label_lengths, const int* input_lengths, const float* grad_scale,
+                                  int alphabet_size, int minibatch, float* costs_device, void* workspace,
+                                  rnntOptions options) {
+    if (!activations || !flat_labels || !label_lengths || !input_lengths || !costs_device || !workspace ||
+        alphabet_size <= 0 || minibatch <= 0 || options.maxT <= 0 || options.maxU <= 0)
+        return RNNT_STATUS_INVALID_VALUE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(options.stream);
+    rnntStatus_t st = loss_op<float>(activations, gradients, flat_labels, label_lengths, input_lengths, grad_scale,
+                                     alphabet_size, minibatch, options.maxT, options.maxU, options.blank_label,
+                                     workspace, s);
+    if (st) return st;
+    LossWs<float> w(workspace, minibatch, options.maxT, options.maxU);
+    negate_kernel<<<(minibatch + 127) / 128, 128, 0, s>>>(w.llf, costs_device, minibatch);
+    RB_LAUNCHED(1);
+    return check_launch();
+}
+
+rnntStatus_t rnntb200_joint_workspace_size(const rnntb200JointDesc* desc, size_t* size_bytes) {
+    if (!desc_ok(desc) || !size_bytes) return RNNT_STATUS_INVALID_VALUE;
+    JointWs ws(*desc, nullptr);
+    *size_bytes = ws.total;
+    return RNNT_STATUS_SUCCESS;
+}
+
+rnntStatus_t rnntb200_joint_loss_forward(const rnntb200JointDesc* desc, const float* enc, const float* pred,
+                                         const float* W, const float* bias, const int* labels,
+                                         const int* label_lengths, const int* input_lengths, float* costs,
+                                         void* workspace) {
+    if (!desc_ok(desc) || !enc || !pred || !W || !bias || !labels || !label_lengths || !input_lengths || !costs ||
+        !workspace)
+        return RNNT_STATUS_INVALID_VALUE;
+    const rnntb200JointDesc& d = *desc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(d.stream);
+    JointWs ws(d, workspace);
+    rnntStatus_t st;
+    if (d.precision == RNNTB200_FP32_EXACT) {
+        st = exact_forward(d, ws, enc, pred, W, bias, labels, label_lengths, input_lengths, s);
+    } else {
+#ifndef RNNTB200_NO_TC
+        unsigned nl = 0;
+        st = rb::tc_forward(d, ws.scratch, enc, pred, W, bias, labels, label_lengths, input_lengths, ws.loss.lse,
+                            ws.loss.lpb, ws.loss.lpl, s, &nl);
+        RB_LAUNCHED(nl);
+#else
+        fprintf(stderr, "rnnt_b200: built without the tcgen05 path\n");
+        st = RNNT_STATUS_EXECUTION_FAILED;
+#endif
+    }
+    if (st) return st;
+    st = launch_alpha_beta(ws.loss, input_lengths, label_lengths, d.B, d.maxT, d.maxU, s);
+    if (st) return st;
+    negate_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.loss.llf, costs, d.B);
+    RB_LAUNCHED(1);
+    return check_launch();
+}
+
+rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const float* enc, const float* pred,
+                                          const float* W, const float* bias, const int* labels,
+                                          const int* label_lengths, const int* input_lengths,
+                                          const float* grad_costs, float* d_enc, float* d_pred, float* dW,
+                                          float* db, void* workspace) {
+    if (!desc_ok(desc) || !enc || !pred || !W || !bias || !labels || !label_lengths || !input_lengths ||
+        !grad_costs || !d_enc || !d_pred || !dW || !db || !workspace)
+        return RNNT_STATUS_INVALID_VALUE;
+    const rnntb200JointDesc& d = *desc;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(d.stream);
+    JointWs ws(d, workspace);
+    if (d.precision == RNNTB200_FP32_EXACT)
+        return exact_backward(d, ws, enc, pred, W, bias, labels, label_lengths, input_lengths, grad_costs, d_enc,
+                              d_pred, dW, db, s);
+#ifndef RNNTB200_NO_TC
+    const long long N = (long long)d.B * d.maxT * d.maxU;
+    rb::cell_coef_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(
+        N, input_lengths, label_lengths, d.maxT, d.maxU, skew_plane(d.maxT, d.maxU), ws.loss.lse, ws.loss.lpb,
+        ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf, grad_costs, ws.coef);
+    RB_LAUNCHED(1);
+    if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    unsigned nl = 0;
+    rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, W, bias, labels, label_lengths, input_lengths,
+                                      ws.loss.lse, ws.coef, d_enc, d_pred, dW, db, s, &nl);
+    RB_LAUNCHED(nl);
+    return st;
+#else
+    fprintf(stderr, "rnnt_b200: built without the tcgen05 path\n");
+    return RNNT_STATUS_EXECUTION_FAILED;
+#endif
+}
+
+rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* enc, const float* pred,
+                                   const float* W, const float* bias, float* logits, void* workspace) {
+    if (!desc_ok(desc) || !enc || !pred || !W || !bias || !logits || !workspace) return RNNT_STATUS_INVALID_VALUE;
+    rnntb200JointDesc d = *desc;
+    d.precision = RNNTB200_FP32_EXACT;  // the materialising entry is the fp32 literal of model.py:158-166
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(d.stream);
+    JointWs ws(d, workspace);
+    const long long N = (long long)d.B * d.maxT * d.maxU;
+    float* Z = reinterpret_cast<float*>(ws.scratch);
+    for (long long r0 = 0; r0 < N; r0 += ws.chunk_rows) {
+        const long long rows = (N - r0 < ws.chunk_rows) ? N - r0 : ws.chunk_rows;
+        rb::zgen_kernel<<<ew_blocks(rows * d.H), 256, 0, s>>>(enc, pred, Z, r0, rows, d.maxT, d.maxU, d.H);
+        launch_sgemm_zw(Z, W, bias, logits + r0 * d.V, rows, d.H, d.V, s);
+        RB_LAUNCHED(1);
+        if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+unsigned long long rnntb200_launch_count() { return g_launches.load(); }
+
+const char* rnntb200_build_info() {
+#ifndef RNNTB200_NO_TC
+    return "rnnt_b200 0.1 sm_100a tcgen05=1";
+#else
+    return "rnnt_b200 0.1 sm_100a tcgen05=0";
+#endif
+}
+
+}  // extern "C"

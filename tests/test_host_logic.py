@@ -1,0 +1,60 @@
+"""Host-side logic of the reference-facing Python surface (no GPU needed)."""
+import numpy as np
+import pytest
+import torch
+
+import rnnt_speech_recognition_b200 as rb
+
+
+def i32(*v):
+    return torch.tensor(v, dtype=torch.int32)
+
+
+def test_encoder_lengths_is_ceil_of_true_division():
+    # utils/loss.py:31-33 -- tf.math.ceil(spec_lengths / reduction_factor) -> int32
+    spec = torch.tensor([1, 2, 3, 4, 5, 1023, 1024, 1025])
+    assert rb.encoder_lengths(spec, 2).tolist() == [1, 1, 2, 2, 3, 512, 512, 513]
+    assert rb.encoder_lengths(spec, 1).tolist() == spec.tolist()
+    assert rb.encoder_lengths(spec, 3).dtype == torch.int32
+
+
+def test_certify_inputs_messages():
+    acts = torch.zeros(2, 4, 3, 5)
+    lab, tl, ll = torch.zeros(2, 2, dtype=torch.int32), i32(4, 4), i32(2, 2)
+    rb.certify_inputs(acts, lab, tl, ll)
+    with pytest.raises(TypeError, match="labels must be"):
+        rb.certify_inputs(acts, lab.long(), tl, ll)
+    with pytest.raises(TypeError, match="lengths must be"):
+        rb.certify_inputs(acts, lab, tl.long(), ll)
+    with pytest.raises(ValueError, match="must be contiguous"):
+        rb.certify_inputs(acts.transpose(1, 2), lab, tl, ll)
+    with pytest.raises(ValueError, match="must have a length per example"):
+        rb.certify_inputs(acts, lab, i32(4), ll)
+    with pytest.raises(ValueError, match="log_probs must be 4D"):
+        rb.certify_inputs(acts[0], lab, i32(4, 4, 4, 4), i32(2, 2, 2, 2))
+    with pytest.raises(ValueError, match="Input length mismatch"):
+        rb.certify_inputs(acts, lab, i32(3, 3), ll)
+    with pytest.raises(ValueError, match="Output length mismatch"):
+        rb.certify_inputs(acts, lab, tl, i32(1, 1))
+
+
+def test_no_cpu_fallback():
+    acts = torch.zeros(1, 2, 3, 5, requires_grad=True)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rb.rnnt_loss(acts, torch.zeros(1, 2, dtype=torch.int32), i32(2), i32(2))
+    loss_fn = rb.get_loss_fn(2)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        loss_fn(torch.zeros(1, 2), acts, torch.tensor([4]), torch.tensor([2]))
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        rb.joint_rnnt_loss(torch.zeros(1, 2, 8), torch.zeros(1, 3, 8), torch.zeros(8, 5), torch.zeros(5),
+                           torch.zeros(1, 2, dtype=torch.int32), i32(2), i32(2))
+
+
+def test_joint_module_parameters_follow_keras_layout():
+    j = rb.Joint(proj_size=12, joint_net_size=16, vocab_size=10)
+    assert j.kernel_1.shape == (12, 16) and j.kernel_2.shape == (16, 10)      # Dense kernel is (in, out)
+    f, g = torch.randn(2, 5, 12), torch.randn(2, 3, 12)
+    e, p = j.hoist(f, g)
+    want = torch.tanh((f[:, :, None] + g[:, None]) @ j.kernel_1 + j.bias_1)   # model.py:158-163 literally
+    got = torch.tanh(e[:, :, None] + p[:, None])
+    assert torch.allclose(got, want, atol=1e-5)
