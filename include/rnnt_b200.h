@@ -164,6 +164,13 @@ rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* e
 /** Number of kernels launched by this library in this process since load (bench.py's gpu_launches). */
 unsigned long long rnntb200_launch_count();
 
+/** Per-kernel CUDA-event instrumentation for bench.py's attribution pass.  set_timing(1) clears the record
+ *  list and enables recording (events on the launching stream around each hot kernel); set_timing(0)
+ *  disables and clears.  After synchronising the stream, get_timing(i, &name, &ms) returns 1 and the i-th
+ *  record, or 0 past the end.  Off by default; never enabled inside a timed benchmark region. */
+void rnntb200_set_timing(int on);
+int rnntb200_get_timing(int index, const char** name, float* ms);
+
 /** Build info string: "rnnt_b200 <version> sm_100a tcgen05=<0|1>". */
 const char* rnntb200_build_info();
 

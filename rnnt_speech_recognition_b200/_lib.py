@@ -28,7 +28,7 @@ class JointDesc(C.Structure):
 EXPORTS = ("get_warprnnt_version", "rnntGetStatusString", "get_workspace_size", "compute_rnnt_loss",
            "compute_rnnt_loss_fp64", "rnntb200_loss_device", "rnntb200_joint_workspace_size",
            "rnntb200_joint_loss_forward", "rnntb200_joint_loss_backward", "rnntb200_joint_logits",
-           "rnntb200_launch_count", "rnntb200_build_info")
+           "rnntb200_launch_count", "rnntb200_build_info", "rnntb200_set_timing", "rnntb200_get_timing")
 
 _lib = None
 
@@ -63,6 +63,9 @@ def load(build_if_missing=True):
     L.rnntb200_joint_logits.argtypes = [C.POINTER(JointDesc)] + [vp] * 6
     L.rnntb200_launch_count.restype = C.c_ulonglong
     L.rnntb200_build_info.restype = C.c_char_p
+    L.rnntb200_set_timing.argtypes = [ci]
+    L.rnntb200_set_timing.restype = None
+    L.rnntb200_get_timing.argtypes = [ci, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]
     _lib = L
     return L
 
@@ -74,3 +77,17 @@ def check(status, what):
 
 def launch_count():
     return int(load().rnntb200_launch_count())
+
+
+def set_timing(on):
+    load().rnntb200_set_timing(int(bool(on)))
+
+
+def get_timings():
+    """[(kernel name, milliseconds)] recorded since set_timing(True); synchronise the stream first."""
+    L, out, i = load(), [], 0
+    name, ms = C.c_char_p(), C.c_float()
+    while L.rnntb200_get_timing(i, C.byref(name), C.byref(ms)):
+        out.append((name.value.decode(), ms.value))
+        i += 1
+    return out

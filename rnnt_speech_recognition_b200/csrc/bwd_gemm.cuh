@@ -1,0 +1,41 @@
+// bwd_gemm.cuh -- the two plain GEMMs of the bf16 backward over the materialised bf16 dlogits rows:
+//     dZ[rows,H]  = dl[rows,V] . Wb[H,V]^T          (fp32 out)
+//     dW[H,V]    (+)= zb[rows,H]^T . dl[rows,V]     (fp32 out, accumulated across utterance chunks)
+// RNNTB200_BWD_CUBLAS: interim library path (cuBLAS is allowed for PLAIN GEMMs; these two have no
+// fused prologue/epilogue).  It is the baseline the hand-written tcgen05 kernels are checked against.
+#pragma once
+#include <cublas_v2.h>
+
+namespace rb {
+
+inline cublasHandle_t tc_cublas() {
+    static cublasHandle_t h = nullptr;
+    if (!h && cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+    return h;
+}
+
+inline rnntStatus_t bwd_gemms(const rnntb200JointDesc& d, const TcGeom& g, const TcScratch& sc, const RowMap& m,
+                              int nb, size_t rows, const int* xlen, const int* ylen, float* dW, bool accumulate,
+                              cudaStream_t s, unsigned* launches) {
+    (void)g; (void)m; (void)nb; (void)xlen; (void)ylen;
+    cublasHandle_t h = tc_cublas();
+    if (!h || cublasSetStream(h, s) != CUBLAS_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+    const float one = 1.f, zero = 0.f, beta = accumulate ? 1.f : 0.f;
+    ScopedTimer* t = new ScopedTimer("gemm dZ=dl.W^T (cublas)", s);
+    // row-major dZ[rows,H] == column-major [H,rows] = Wb_cm[V,H]^T . dl_cm[V,rows]
+    if (cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, d.H, (int)rows, d.V, &one, sc.Wb, CUDA_R_16BF, d.V, sc.dl,
+                     CUDA_R_16BF, d.V, &zero, sc.dz, CUDA_R_32F, d.H, CUBLAS_COMPUTE_32F,
+                     CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
+        return RNNT_STATUS_EXECUTION_FAILED;
+    delete t; t = new ScopedTimer("gemm dW=z^T.dl (cublas)", s);
+    // row-major dW[H,V] == column-major [V,H] = dl_cm[V,rows] . zb_cm[H,rows]^T
+    if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, d.V, d.H, (int)rows, &one, sc.dl, CUDA_R_16BF, d.V, sc.zb,
+                     CUDA_R_16BF, d.H, &beta, dW, CUDA_R_32F, d.V, CUBLAS_COMPUTE_32F,
+                     CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
+        return RNNT_STATUS_EXECUTION_FAILED;
+    delete t;
+    *launches += 2;
+    return RNNT_STATUS_SUCCESS;
+}
+
+}  // namespace rb

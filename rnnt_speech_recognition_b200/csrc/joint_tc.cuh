@@ -1,0 +1,569 @@
+// joint_tc.cuh -- bf16 tensor-core (tcgen05 / TMEM / TMA) kernels of the fused joint + loss path.
+//
+// joint_tc_kernel<MODE>: one persistent CTA per SM, each looping over 128-cell lattice tiles
+// (TT time steps x UU label positions of one utterance).  Per tile:
+//   * 8 producer warps form the A operand  z = tanh(enc[b,t,:] + pred[b,u,:])  (bf16) straight into
+//     shared memory in the canonical K-major SWIZZLE_128B layout (H/64 K-blocks of 128x64) -- the
+//     (B,T,U,H) activation tensor of model.py:158-163 never exists in HBM;
+//   * one TMA thread streams W^T (bf16, V x H, K-major) tiles [NC x 64] through an mbarrier ring;
+//   * one MMA thread issues tcgen05.mma (M=128, N=NC, K=16) into double-buffered TMEM accumulators;
+//   * 4 epilogue warps read the accumulators with tcgen05.ld (thread = lattice cell) and
+//       MODE 0 (forward):  add bias, ONLINE log-sum-exp across the V chunks, pick logit[blank] and
+//                          logit[label_u]  ->  lse (natural order), lp_blank / lp_label (skewed planes)
+//                          -- the (B,T,U,V) logits of model.py:165-166 never reach HBM;
+//       MODE 1 (backward): dlogit = g*exp(x + kd) - [blank] g*sb - [label] g*sl  (coefficients from
+//                          cell_coef_kernel) -> bf16 rows of the dlogits workspace (+ bf16 z rows).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+
+#include "../../include/rnnt_b200.h"
+#include "kernels_simt.cuh"
+#include "ptx.cuh"
+#include "timing.cuh"
+
+namespace rb {
+
+constexpr int TC_THREADS = 320;      // warps 0-3 epilogue+producer, 4-7 producer, 8 TMA, 9 MMA
+constexpr int TC_MAX_KB = 16;        // H <= 1024
+constexpr int TC_MAX_STAGES = 4;
+constexpr int TC_TMEM_COLS = 512;
+
+struct TcGeom {
+    int TT, UU, nTb, nUb;  // tile = TT x UU cells (TT*UU == 128); tiles per utterance
+    int NC, NCH, KB, stages;
+    size_t smem_bytes;
+    bool ok;
+};
+
+inline TcGeom tc_geometry(int maxT, int maxU, int H, int V) {
+    TcGeom g{};
+    g.ok = false;
+    if (H % 64 || V % 64 || H > 64 * TC_MAX_KB) return g;
+    int best = 128, best_pad = 1 << 30;
+    for (int uu = 128; uu >= 8; uu >>= 1) {  // least padding along U, ties -> widest
+        const int pad = (maxU + uu - 1) / uu * uu;
+        if (pad < best_pad) { best_pad = pad; best = uu; }
+    }
+    g.UU = best;
+    g.TT = 128 / best;
+    g.nTb = (maxT + g.TT - 1) / g.TT;
+    g.nUb = (maxU + g.UU - 1) / g.UU;
+    g.KB = H / 64;
+    const size_t zbytes = (size_t)g.KB * 16384, limit = 232448 - 1024 /*alignment slack*/ - 512 /*barriers*/;
+    for (int nc = 256; nc >= 64; nc >>= 1) {
+        if (V % nc) continue;
+        for (int st = TC_MAX_STAGES; st >= 2; --st) {
+            if (zbytes + (size_t)st * nc * 128 <= limit) {
+                g.NC = nc; g.NCH = V / nc; g.stages = st;
+                g.smem_bytes = zbytes + (size_t)st * nc * 128 + 512 + 1024;
+                g.ok = true;
+                return g;
+            }
+        }
+    }
+    return g;
+}
+
+struct JointTcParams {
+    const float* enc; const float* pred; const float* bias;
+    const int* labels; const int* xlen; const int* ylen;
+    int B, maxT, maxU, H, V, blank;
+    int TT, UU, nTb, nUb, NC, NCH, KB, stages;
+    long long SK;
+    int b0, nb;                 // utterance range of this launch
+    float* lse; float* lpb; float* lpl;              // MODE 0 outputs
+    const float4* coef; __nv_bfloat16* dl; __nv_bfloat16* zb;  // MODE 1: coefficients in, dlogits / z rows out
+};
+
+struct TileInfo { int b, t0, u0, Tn, Un; bool valid; };
+__device__ __forceinline__ TileInfo decode_tile(const JointTcParams& p, int tile) {
+    TileInfo ti;
+    const int per_utt = p.nTb * p.nUb;
+    const int bl = tile / per_utt, rem = tile - bl * per_utt;
+    ti.b = p.b0 + bl;
+    ti.t0 = (rem / p.nUb) * p.TT;
+    ti.u0 = (rem % p.nUb) * p.UU;
+    ti.Tn = p.xlen[ti.b];
+    ti.Un = p.ylen[ti.b] + 1;
+    ti.valid = ti.t0 < ti.Tn && ti.u0 < ti.Un;
+    return ti;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_constant__ CUtensorMap tmap_wt,
+                                                                 const JointTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KB = p.KB, NC = p.NC, NCH = p.NCH, stages = p.stages;
+    uint8_t* zs = smem;                                   // KB x [128 x 64] bf16, SW128 K-major
+    uint8_t* wsm = smem + (size_t)KB * 16384;             // stages x [NC x 64] bf16, SW128 K-major (TMA)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * NC * 128);
+    uint64_t* z_full = bars;                              // [TC_MAX_KB]  producers -> MMA
+    uint64_t* z_free = bars + TC_MAX_KB;                  //              MMA -> producers (tile's MMAs retired)
+    uint64_t* w_full = z_free + 1;                        // [stages]     TMA -> MMA
+    uint64_t* w_empty = w_full + TC_MAX_STAGES;           // [stages]     MMA -> TMA
+    uint64_t* acc_full = w_empty + TC_MAX_STAGES;         // [2]          MMA -> epilogue
+    uint64_t* acc_empty = acc_full + 2;                   // [2]          epilogue -> MMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_MAX_KB; ++i) ptx::mbar_init(&z_full[i], 8);
+        ptx::mbar_init(z_free, 1);
+        for (int i = 0; i < TC_MAX_STAGES; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 9) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp == 8 && lane == 0) ptx::prefetch_tmap(&tmap_wt);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int ntiles = p.nb * p.nTb * p.nUb;
+
+    if (warp == 8) {
+        // ===================== TMA producer: W^T tiles [NC rows (v) x 64 (k)] =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (!decode_tile(p, tile).valid) continue;
+                for (int c = 0; c < NCH; ++c)
+                    for (int kb = 0; kb < KB; ++kb) {
+                        ptx::mbar_wait(&w_empty[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[stage], (uint32_t)NC * 128);
+                        ptx::tma_load_2d(wsm + (size_t)stage * NC * 128, &tmap_wt, &w_full[stage], kb * 64, c * NC);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 9) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
+            int stage = 0; uint32_t phase = 0, g = 0, it = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (!decode_tile(p, tile).valid) continue;
+                for (int c = 0; c < NCH; ++c, ++g) {
+                    const uint32_t buf = g & 1;
+                    ptx::mbar_wait(&acc_empty[buf], ((g >> 1) & 1) ^ 1);
+                    ptx::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + buf * NC;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (c == 0) ptx::mbar_wait(&z_full[kb], it & 1);
+                        ptx::mbar_wait(&w_full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t a0 = ptx::smem_u32(zs + (size_t)kb * 16384);
+                        const uint32_t b0 = ptx::smem_u32(wsm + (size_t)stage * NC * 128);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a0 + k * 32),
+                                           ptx::umma_desc_k_sw128(b0 + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                        ptx::umma_commit(&w_empty[stage]);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+                    ptx::umma_commit(&acc_full[buf]);
+                }
+                ptx::umma_commit(z_free);
+                ++it;
+            }
+        }
+    } else {
+        // ===================== 8 compute warps: z producers (all) + epilogue (warps 0-3) =====================
+        constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        uint32_t g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const TileInfo ti = decode_tile(p, tile);
+            if (!ti.valid) continue;
+            // ---- A operand: z = tanh(enc + pred) -> bf16, SW128 K-major, one 16-byte chunk per thread-task
+            ptx::mbar_wait(z_free, (it & 1) ^ 1);
+            for (int kb = 0; kb < KB; ++kb) {
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    const int r = pass * 32 + warp * 4 + (lane >> 3), ch = lane & 7;
+                    const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+                    uint4 packed = make_uint4(0u, 0u, 0u, 0u);
+                    if (t < ti.Tn && u < ti.Un) {
+                        const int k = kb * 64 + ch * 8;
+                        const float4* e = reinterpret_cast<const float4*>(p.enc + ((size_t)ti.b * p.maxT + t) * p.H + k);
+                        const float4* q = reinterpret_cast<const float4*>(p.pred + ((size_t)ti.b * p.maxU + u) * p.H + k);
+                        const float4 e0 = __ldg(e), e1 = __ldg(e + 1), q0 = __ldg(q), q1 = __ldg(q + 1);
+                        packed.x = ptx::pack_bf16x2(ptx::tanh_approx(e0.x + q0.x), ptx::tanh_approx(e0.y + q0.y));
+                        packed.y = ptx::pack_bf16x2(ptx::tanh_approx(e0.z + q0.z), ptx::tanh_approx(e0.w + q0.w));
+                        packed.z = ptx::pack_bf16x2(ptx::tanh_approx(e1.x + q1.x), ptx::tanh_approx(e1.y + q1.y));
+                        packed.w = ptx::pack_bf16x2(ptx::tanh_approx(e1.z + q1.z), ptx::tanh_approx(e1.w + q1.w));
+                    }
+                    *reinterpret_cast<uint4*>(zs + (size_t)kb * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = packed;
+                    if (MODE == 1 && p.zb) {
+                        const size_t row = ((size_t)(tile)) * 128 + r;
+                        *reinterpret_cast<uint4*>(p.zb + row * p.H + kb * 64 + ch * 8) = packed;
+                    }
+                }
+                ptx::fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&z_full[kb]);
+            }
+            // ---- epilogue: thread = lattice cell (TMEM lane), warps 0-3 cover lanes 0..127
+            if (warp < 4) {
+                const int r = warp * 32 + lane;
+                const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+                const bool rv = t < ti.Tn && u < ti.Un;
+                const int lab = (rv && u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
+                const long long cell = ((long long)ti.b * p.maxT + t) * p.maxU + u;
+                float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f;  // MODE 0 state (log2 domain)
+                float kd2 = -CUDART_INF_F, cg = 0.f, csb = 0.f, csl = 0.f;  // MODE 1 coefficients
+                if (MODE == 1 && rv) {
+                    const float4 cf = p.coef[cell];
+                    kd2 = cf.x * LOG2E; cg = cf.y; csb = cf.z; csl = cf.w;
+                }
+                const uint32_t lane_addr = tmem_base + ((uint32_t)(warp * 32) << 16);
+                for (int c = 0; c < NCH; ++c, ++g) {
+                    const uint32_t buf = g & 1;
+                    ptx::mbar_wait(&acc_full[buf], (g >> 1) & 1);
+                    ptx::tc_fence_after();
+                    for (int j = 0; j < NC / 32; ++j) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(lane_addr + buf * NC + j * 32, v);
+                        ptx::tmem_ld_wait();
+                        const int col0 = c * NC + j * 32;
+                        // one coalesced bias load per warp, broadcast lane-by-lane (a per-element LDG would
+                        // saturate the LSU long before the MMA pipe)
+                        const float bv = __ldg(p.bias + col0 + lane) * LOG2E;
+                        float y[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
+                        if (MODE == 0) {
+                            float gm = y[0];
+#pragma unroll
+                            for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
+                            const float mn = fmaxf(m2, gm);
+                            float acc = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) acc += ptx::ex2_approx(y[i] - mn);
+                            s = s * ptx::ex2_approx(m2 - mn) + acc;
+                            m2 = mn;
+                            if (p.blank >= col0 && p.blank < col0 + 32) {  // uniform
+#pragma unroll
+                                for (int i = 0; i < 32; ++i)
+                                    if (col0 + i == p.blank) yb = y[i];
+                            }
+                            const int d = lab - col0;
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) yl = (i == d) ? y[i] : yl;
+                        } else {
+                            const int d = lab - col0, db = p.blank - col0;
+                            uint32_t o[16];
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                float d0 = cg * ptx::ex2_approx(y[i] + kd2);
+                                float d1 = cg * ptx::ex2_approx(y[i + 1] + kd2);
+                                if (i == db) d0 -= csb;
+                                if (i + 1 == db) d1 -= csb;
+                                if (i == d) d0 -= csl;
+                                if (i + 1 == d) d1 -= csl;
+                                o[i >> 1] = ptx::pack_bf16x2(d0, d1);
+                            }
+                            uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
+                            dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                            dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                            dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                            dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                        }
+                    }
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+                }
+                if (MODE == 0 && rv) {
+                    const float lse2 = m2 + log2f(s);
+                    p.lse[cell] = lse2 * LN2;
+                    const long long k = sk_index(ti.b, t, u, p.maxU, p.SK);
+                    p.lpb[k] = (yb - lse2) * LN2;
+                    if (u < ti.Un - 1) p.lpl[k] = (yl - lse2) * LN2;
+                }
+            } else {
+                g += NCH;
+            }
+            ++it;
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 9) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+// W (H,V) fp32 -> Wt (V,H) bf16 [B operand of the logits GEMM, K=h] and Wb (H,V) bf16 [B operand of dZ, K=v]
+__global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt,
+                                                        __nv_bfloat16* __restrict__ Wb, int H, int V) {
+    __shared__ float tile[32][33];
+    const int v0 = blockIdx.x * 32, h0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int h = h0 + i, v = v0 + tx;
+        const float w = (h < H && v < V) ? W[(size_t)h * V + v] : 0.f;
+        tile[i][tx] = w;
+        if (h < H && v < V) Wb[(size_t)h * V + v] = __float2bfloat16(w);
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int v = v0 + i, h = h0 + tx;
+        if (h < H && v < V) Wt[(size_t)v * H + h] = __float2bfloat16(tile[tx][i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reductions of the backward (tile-ordered rows: row = tile*128 + (t%TT)*UU + (u%UU)).
+//   g = dZ * sech^2(enc+pred), with sech^2 evaluated from exp (relative accuracy near |z| -> 1,
+//   where 1 - tanh^2 computed from a rounded tanh would lose all its digits)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float sech2(float x) {
+    const float e = ptx::ex2_approx(-2.8853900817779268f * fabsf(x));  // exp(-2|x|)
+    const float d = 1.f + e;
+    return 4.f * e / (d * d);
+}
+struct RowMap { int TT, UU, nTb, nUb, b0; };
+__device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u) {
+    const size_t q = ((size_t)(b - m.b0) * m.nTb + t / m.TT) * m.nUb + u / m.UU;
+    return q * 128 + (t % m.TT) * m.UU + (u % m.UU);
+}
+// d_pred[b,u,:] = sum_t g ; grid (ceil(H/128), maxU, nb), block 128 (threads along h)
+__global__ void __launch_bounds__(128) dpred_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+                                                    const float* __restrict__ pred, const int* __restrict__ xlen,
+                                                    const int* __restrict__ ylen, RowMap m, int maxT, int maxU, int H,
+                                                    float* __restrict__ d_pred) {
+    const int h = blockIdx.x * 128 + threadIdx.x, u = blockIdx.y, b = m.b0 + blockIdx.z;
+    if (h >= H) return;
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    float acc = 0.f;
+    if (u < Un) {
+        const float pv = pred[((size_t)b * maxU + u) * H + h];
+        for (int t = 0; t < Tn; ++t)
+            acc += dz[tile_row(m, b, t, u) * H + h] * sech2(enc[((size_t)b * maxT + t) * H + h] + pv);
+    }
+    d_pred[((size_t)b * maxU + u) * H + h] = acc;
+}
+// d_enc[b,t,:] = sum_u g ; grid (ceil(H/128), maxT, nb)
+__global__ void __launch_bounds__(128) denc_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+                                                   const float* __restrict__ pred, const int* __restrict__ xlen,
+                                                   const int* __restrict__ ylen, RowMap m, int maxT, int maxU, int H,
+                                                   float* __restrict__ d_enc) {
+    const int h = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = m.b0 + blockIdx.z;
+    if (h >= H) return;
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    float acc = 0.f;
+    if (t < Tn) {
+        const float ev = enc[((size_t)b * maxT + t) * H + h];
+        for (int u = 0; u < Un; ++u)
+            acc += dz[tile_row(m, b, t, u) * H + h] * sech2(ev + pred[((size_t)b * maxU + u) * H + h]);
+    }
+    d_enc[((size_t)b * maxT + t) * H + h] = acc;
+}
+// db[v] += sum over VALID tiles' rows of dl[row, v] (bf16 rows); grid (V/64, nsplit), block 256 = 64 cols x 4 row lanes
+__global__ void __launch_bounds__(256) db_kernel(const __nv_bfloat16* __restrict__ dl, const int* __restrict__ xlen,
+                                                 const int* __restrict__ ylen, RowMap m, int nb, int V,
+                                                 float* __restrict__ db) {
+    const int v = blockIdx.x * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
+    const int ntiles = nb * m.nTb * m.nUb, per_utt = m.nTb * m.nUb;
+    float acc = 0.f;
+    for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
+        const int bl = tile / per_utt, rem = tile - bl * per_utt, b = m.b0 + bl;
+        if ((rem / m.nUb) * m.TT >= xlen[b] || (rem % m.nUb) * m.UU >= ylen[b] + 1) continue;  // tile never written
+        const __nv_bfloat16* base = dl + (size_t)tile * 128 * V + v;
+        for (int r = rl; r < 128; r += 4) acc += __bfloat162float(base[(size_t)r * V]);
+    }
+    __shared__ float sm[4][64];
+    sm[rl][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (rl == 0) atomicAdd(db + v, sm[0][v & 63] + sm[1][v & 63] + sm[2][v & 63] + sm[3][v & 63]);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+// 2-D row-major bf16 matrix [rows x cols] (cols contiguous), box [box_rows x 64 cols], SWIZZLE_128B
+inline bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                           uint32_t box_cols = 64) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 2};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+struct TcScratch {
+    __nv_bfloat16 *Wt, *Wb, *dl, *zb;
+    float* dz;
+    int bchunk;          // utterances per backward pass
+    size_t rows_chunk;   // bchunk * tiles_per_utt * 128
+    size_t bytes;
+};
+inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
+    TcScratch s{};
+    const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
+    const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
+    const size_t per_row = (size_t)d.V * 2 + (size_t)d.H * 2 + (size_t)d.H * 4;
+    const size_t budget = (size_t)16 << 30;
+    size_t bc = budget / (rows_utt * per_row);
+    if (bc < 1) bc = 1;
+    if (bc > (size_t)d.B) bc = d.B;
+    s.bchunk = (int)bc;
+    s.rows_chunk = bc * rows_utt;
+    char* p = static_cast<char*>(base);
+    auto take = [&](size_t n) { char* r = p; p += (n + 255) / 256 * 256; return r; };
+    s.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
+    s.Wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
+    s.dl = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.V * 2));
+    s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
+    s.dz = reinterpret_cast<float*>(take(s.rows_chunk * d.H * 4));
+    s.bytes = (size_t)(p - static_cast<char*>(base));
+    return s;
+}
+inline size_t tc_scratch_bytes(const rnntb200JointDesc& d) {
+    if (!tc_geometry(d.maxT, d.maxU, d.H, d.V).ok) return 0;
+    return tc_scratch_layout(d, nullptr).bytes;
+}
+
+inline int tc_num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+inline bool tc_fill_params(const rnntb200JointDesc& d, const TcGeom& g, JointTcParams& p, const float* enc,
+                           const float* pred, const float* bias, const int* labels, const int* ylen,
+                           const int* xlen) {
+    p = JointTcParams{};
+    p.enc = enc; p.pred = pred; p.bias = bias; p.labels = labels; p.xlen = xlen; p.ylen = ylen;
+    p.B = d.B; p.maxT = d.maxT; p.maxU = d.maxU; p.H = d.H; p.V = d.V; p.blank = d.blank_label;
+    p.TT = g.TT; p.UU = g.UU; p.nTb = g.nTb; p.nUb = g.nUb; p.NC = g.NC; p.NCH = g.NCH; p.KB = g.KB;
+    p.stages = g.stages;
+    p.SK = (long long)(d.maxT + d.maxU - 1) * d.maxU;
+    return true;
+}
+
+template <int MODE>
+inline rnntStatus_t tc_launch(const TcGeom& g, const CUtensorMap& tm, const JointTcParams& p, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(joint_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)232448) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
+        attr_set = true;
+    }
+    const int ntiles = p.nb * p.nTb * p.nUb;
+    const int grid = ntiles < tc_num_sms() ? ntiles : tc_num_sms();
+    ScopedTimer tmr(MODE == 0 ? "joint_tc_kernel<fwd>" : "joint_tc_kernel<dlogits>", s);
+    joint_tc_kernel<MODE><<<grid, TC_THREADS, g.smem_bytes, s>>>(tm, p);
+    return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
+}
+
+inline rnntStatus_t tc_unsupported(const rnntb200JointDesc& d) {
+    fprintf(stderr,
+            "rnnt_b200: RNNTB200_BF16_TC needs H %% 64 == 0, V %% 64 == 0 and H <= 640 for the resident-z kernel "
+            "(got H=%d V=%d); use RNNTB200_FP32_EXACT\n", d.H, d.V);
+    return RNNT_STATUS_INVALID_VALUE;
+}
+
+inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
+                               const float* W, const float* bias, const int* labels, const int* ylen,
+                               const int* xlen, float* lse, float* lpb, float* lpl, cudaStream_t s,
+                               unsigned* launches) {
+    const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
+    if (!g.ok) return tc_unsupported(d);
+    TcScratch sc = tc_scratch_layout(d, scratch);
+    convert_w_kernel<<<dim3((d.V + 31) / 32, (d.H + 31) / 32), 256, 0, s>>>(W, sc.Wt, sc.Wb, d.H, d.V);
+    CUtensorMap tm;
+    if (!make_tmap_bf16(&tm, sc.Wt, d.V, d.H, g.NC)) {
+        fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    JointTcParams p;
+    tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
+    p.b0 = 0; p.nb = d.B;
+    p.lse = lse; p.lpb = lpb; p.lpl = lpl;
+    *launches += 2;
+    return tc_launch<0>(g, tm, p, s);
+}
+
+}  // namespace rb
+
+#include "bwd_gemm.cuh"
+
+namespace rb {
+
+inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
+                                const float* W, const float* bias, const int* labels, const int* ylen,
+                                const int* xlen, const float* lse, const float4* coef, float* d_enc, float* d_pred,
+                                float* dW, float* db, cudaStream_t s, unsigned* launches) {
+    (void)W; (void)lse;
+    const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
+    if (!g.ok) return tc_unsupported(d);
+    TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
+    CUtensorMap tm;
+    if (!make_tmap_bf16(&tm, sc.Wt, d.V, d.H, g.NC)) return RNNT_STATUS_EXECUTION_FAILED;
+    if (cudaMemsetAsync(db, 0, sizeof(float) * d.V, s) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
+    for (int b0 = 0; b0 < d.B; b0 += sc.bchunk) {
+        const int nb = (d.B - b0 < sc.bchunk) ? d.B - b0 : sc.bchunk;
+        JointTcParams p;
+        tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
+        p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb;
+        const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0};
+        const size_t rows = (size_t)nb * g.nTb * g.nUb * 128;
+        // tiles that lie entirely in the padding are skipped by the kernel; the library GEMMs below reduce
+        // over ALL rows, so those rows must read as zero
+        {
+            ScopedTimer tz("memset(dl,zb)", s);
+            if (cudaMemsetAsync(sc.dl, 0, rows * d.V * 2, s) != cudaSuccess ||
+                cudaMemsetAsync(sc.zb, 0, rows * d.H * 2, s) != cudaSuccess)
+                return RNNT_STATUS_MEMOPS_FAILED;
+        }
+        rnntStatus_t st = tc_launch<1>(g, tm, p, s);
+        if (st) return st;
+        // dZ[rows,H] = dl[rows,V] . Wb[H,V]^T ;  dW[H,V] (+)= zb[rows,H]^T . dl[rows,V]
+        st = bwd_gemms(d, g, sc, m, nb, rows, xlen, ylen, dW, /*accumulate=*/b0 > 0, s, launches);
+        if (st) return st;
+        ScopedTimer* t1 = new ScopedTimer("dpred_kernel", s);
+        dpred_kernel<<<dim3((d.H + 127) / 128, d.maxU, nb), 128, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT,
+                                                                         d.maxU, d.H, d_pred);
+        delete t1; t1 = new ScopedTimer("denc_kernel", s);
+        denc_kernel<<<dim3((d.H + 127) / 128, d.maxT, nb), 128, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT,
+                                                                        d.maxU, d.H, d_enc);
+        delete t1; t1 = new ScopedTimer("db_kernel", s);
+        db_kernel<<<dim3(d.V / 64, 64), 256, 0, s>>>(sc.dl, xlen, ylen, m, nb, d.V, db);
+        delete t1;
+        *launches += 4;
+        if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return RNNT_STATUS_SUCCESS;
+}
+
+}  // namespace rb

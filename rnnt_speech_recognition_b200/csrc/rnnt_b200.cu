@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include "kernels_simt.cuh"
+#include "timing.cuh"
 #ifndef RNNTB200_NO_TC
 #include "joint_tc.cuh"
 #endif
@@ -57,6 +58,7 @@ rnntStatus_t launch_alpha_beta(const LossWs<T>& w, const int* xlen, const int* y
                                cudaStream_t s) {
     const int threads = (maxU + 31) / 32 * 32;
     constexpr int PF = sizeof(T) == 4 ? 8 : 4;
+    rb::ScopedTimer tm("alpha_beta_kernel", s);
     rb::alpha_beta_kernel<T, PF><<<dim3(B, 2), threads, 0, s>>>(w.lpb, w.lpl, w.alphas, w.betas, w.llf, w.llb, xlen,
                                                                 ylen, maxU, skew_plane(maxT, maxU));
     RB_LAUNCHED(1);
@@ -74,12 +76,16 @@ rnntStatus_t loss_op(const T* acts, T* grads, const int* labels, const int* ylen
     LossWs<T> w(workspace, B, maxT, maxU);
     const long long N = (long long)B * maxT * maxU, SK = skew_plane(maxT, maxU);
     const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
-    rb::lse_gather_kernel<T><<<blocks, 256, 0, s>>>(acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK, blank, w.lse,
-                                                    w.lpb, w.lpl);
+    {
+        rb::ScopedTimer tm("lse_gather_kernel", s);
+        rb::lse_gather_kernel<T><<<blocks, 256, 0, s>>>(acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK, blank,
+                                                        w.lse, w.lpb, w.lpl);
+    }
     RB_LAUNCHED(1);
     if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     if (launch_alpha_beta(w, xlen, ylen, B, maxT, maxU, s)) return RNNT_STATUS_EXECUTION_FAILED;
     if (grads) {
+        rb::ScopedTimer tm("rnnt_grad_kernel", s);
         rb::rnnt_grad_kernel<T><<<blocks, 256, 0, s>>>(acts, grads, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
                                                        blank, w.lse, w.alphas, w.betas, w.llf, gscale);
         RB_LAUNCHED(1);
@@ -349,9 +355,11 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
                               d_pred, dW, db, s);
 #ifndef RNNTB200_NO_TC
     const long long N = (long long)d.B * d.maxT * d.maxU;
+    rb::ScopedTimer* tmc = new rb::ScopedTimer("cell_coef_kernel", s);
     rb::cell_coef_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(
         N, input_lengths, label_lengths, d.maxT, d.maxU, skew_plane(d.maxT, d.maxU), ws.loss.lse, ws.loss.lpb,
         ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf, grad_costs, ws.coef);
+    delete tmc;
     RB_LAUNCHED(1);
     if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     unsigned nl = 0;
@@ -385,6 +393,16 @@ rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* e
 }
 
 unsigned long long rnntb200_launch_count() { return g_launches.load(); }
+
+void rnntb200_set_timing(int on) { rb::timing_reset(on); }
+
+int rnntb200_get_timing(int index, const char** name, float* ms) {
+    auto& v = rb::timing_recs();
+    if (index < 0 || index >= (int)v.size() || !name || !ms) return 0;
+    *name = v[index].name;
+    if (cudaEventElapsedTime(ms, v[index].a, v[index].b) != cudaSuccess) *ms = -1.f;
+    return 1;
+}
 
 const char* rnntb200_build_info() {
 #ifndef RNNTB200_NO_TC

@@ -35,11 +35,12 @@ def fp32_tol(costs):
 
     north_star: fp32 rtol = 1e-4.  The absolute floor scales with the cost because every gradient
     entry is exp(alpha + beta + lp - ll) minus (sometimes) another such exponential, and the fp32
-    round-off of an exponent of magnitude O(|ll|) is eps32 * |ll|: the unmodified reference library
-    run in fp32 is itself 3e-5 (|cost| ~ 310) .. 4.5e-5 (|cost| ~ 450) away from its own fp64 run.
+    round-off of an exponent of magnitude O(|ll|) is a few eps32 * |ll|: the UNMODIFIED reference library
+    run in fp32 is itself 3e-5 (|cost| ~ 310), 4.5e-5 (|cost| ~ 450) and 9.6e-4 (|cost| ~ 1540, T=300)
+    away from its own fp64 run -- i.e. up to 6.2e-7 * |cost|; the floor below is 1e-6 * |cost|.
     """
     cmax = float(np.max(np.abs(costs))) if np.size(costs) else 0.0
-    return dict(rtol=1e-4, atol=1e-6 + 4e-7 * cmax)
+    return dict(rtol=1e-4, atol=1e-6 + 1e-6 * cmax)
 
 
 def assert_close(a, b, rtol=1e-4, atol=1e-6, ntol=0.0, what=""):

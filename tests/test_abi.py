@@ -19,7 +19,7 @@ def L():
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "rnnt_b200.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    names = re.findall(r"^\s*(?:rnntStatus_t|int|const char\*|unsigned long long)\s+(\w+)\s*\(", src, flags=re.M)
+    names = re.findall(r"^\s*(?:rnntStatus_t|int|void|const char\*|unsigned long long)\s+(\w+)\s*\(", src, flags=re.M)
     return sorted(set(names))
 
 

@@ -1,0 +1,47 @@
+"""bf16 tensor-core path (tcgen05 fused joint kernels) against the fp64 oracle (small) and the fp32
+exact CUDA path (BASELINE C2 size).  bf16 operands carry 2^-9 relative rounding, so this path is
+held to its own measured tolerance (DESIGN.md "Tolerances"), not to the fp32 rtol 1e-4 gate."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import assert_close
+from test_gpu_joint import run_joint, synth
+
+pytestmark = pytest.mark.gpu
+
+BF16_COST_RTOL = 2e-3
+BF16_GRAD_NTOL = 2e-2     # norm-wise: |err| <= ntol * max|grad|
+
+
+@pytest.mark.parametrize("B,T,U,V,H,seed,ragged", [
+    (2, 20, 8, 64, 64, 0, False),        # one 16x8 tile shape, single K block, single V chunk
+    (3, 37, 19, 128, 128, 1, True),      # ragged, partially filled tiles
+    (2, 50, 40, 192, 320, 2, True),      # V chunk of 64 x3, 5 K blocks
+    (1, 9, 140, 64, 64, 3, False),       # U > 128: two u-blocks per time step
+    (2, 33, 128, 512, 640, 4, True),     # the BASELINE C3 tile geometry (1x128 tiles, 10 K blocks, NC=256)
+])
+def test_bf16_vs_oracle(oracle, B, T, U, V, H, seed, ragged):
+    k = synth(B, T, U, V, H, seed, ragged)
+    gs = np.linspace(0.5, 1.5, B)
+    o = oracle.joint_loss_grad(*(k[n].astype(np.float64) for n in ("enc", "pred", "W", "b")), k["labels"],
+                               k["input_lengths"], k["label_lengths"], 0, grad_scale=gs)
+    costs, grads = run_joint(k, "bf16", scale=gs)
+    assert_close(costs, o["costs"], rtol=BF16_COST_RTOL, atol=1e-2, what="costs")
+    for g, n in zip(grads, ("d_enc", "d_pred", "dW", "db")):
+        assert_close(g, o[n], rtol=0, atol=0, ntol=BF16_GRAD_NTOL, what=n)
+    # padded positions of d_enc / d_pred are exactly zero
+    for b in range(B):
+        assert not grads[0][b, k["input_lengths"][b]:].any()
+        assert not grads[1][b, k["label_lengths"][b] + 1:].any()
+
+
+def test_bf16_vs_fp32_at_c2():
+    k = synth(16, 256, 64, 256, 320, 5, ragged=True)
+    c32, g32 = run_joint(k, "fp32")
+    c16, g16 = run_joint(k, "bf16")
+    assert_close(c16, c32, rtol=BF16_COST_RTOL, atol=1e-2, what="costs")
+    for a, b, n in zip(g16, g32, ("d_enc", "d_pred", "dW", "db")):
+        assert_close(a, b, rtol=0, atol=0, ntol=BF16_GRAD_NTOL, what=n)
+        rel = np.linalg.norm(a - b) / np.linalg.norm(b)
+        assert rel < 1e-2, (n, rel)
