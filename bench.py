@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- RNN-T loss+grad utterances/sec (BASELINE.json metric) on N B200s of one node.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path on the host cores
+
+A "step" is one pass of the hot path (joint forward -> alpha/beta -> gradients to enc_acts, pred_acts,
+W, b) over one synthetic batch of the BASELINE C3 shape (B=32,T=512,U=128,V=1024,H=640 per GPU, bf16
+tensor-core path; --workload c2 runs the fp32 C2 shape).  Weak scaling: every rank holds a full
+batch; the only collective is ONE packed all-reduce of [loss_sum | dW | db] per step.
+
+Printed JSON (one line, rank 0): see the task contract -- value (inputs resident in HBM), e2e (host
+buffers through the public torch API, H2D/D2H inside the timed region), roofline of the dominant
+kernel (CUDA events on the launching stream, attribution pass outside the timed region),
+cpu_baseline (reference library + torch-CPU joint on the host cores), clocks, gpu_launches.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "c3": dict(B=32, T=512, U=128, V=1024, H=640, precision="bf16", dtype="bf16"),
+    "c2": dict(B=16, T=256, U=64, V=256, H=320, precision="fp32", dtype="f32"),
+    "c1": dict(B=2, T=20, U=8, V=32, H=64, precision="fp32", dtype="f32"),
+}
+METRIC = "rnnt_loss_grad_utterances_per_sec"
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def synth(cfg, seed, device, pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    d = dict(enc=torch.randn(B, T, H, generator=g), pred=torch.randn(B, U, H, generator=g),
+             W=torch.randn(H, V, generator=g) / H ** 0.5, b=torch.zeros(V),
+             labels=torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32),
+             il=torch.full((B,), T, dtype=torch.int32), ll=torch.full((B,), U - 1, dtype=torch.int32))
+    if pin:
+        return {k: v.pin_memory() for k, v in d.items()}
+    return {k: v.to(device) for k, v in d.items()}
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.rows.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        reasons = []
+        for i, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap")):
+            if any(len(r) >= 8 and r[i].lower().startswith("active") for r in self.rows):
+                reasons.append(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the reference's own CPU implementation of the path on the host cores
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_runner(cfg):
+    """Returns (run(n_utts) -> seconds, kind, cores, note).  What run_rnnt.py executes on a CPU-only
+    TF build: joint forward (model.py:158-166) -> log_softmax (utils/loss.py:29-30) ->
+    compute_rnnt_loss(RNNT_CPU) -> backward to d_enc, d_pred, dW, db.  The loss library is the
+    UNMODIFIED reference (oracle/_ref/libwarprnnt.so) when it was built; TensorFlow 2.2 is not
+    installable here, so the Dense/tanh/log_softmax/autograd pieces run as torch-CPU fp32 ops on all
+    host threads.  Without oracle/_ref the C oracle port (oracle/rnnt_oracle.c) stands in."""
+    import numpy as np
+    import torch
+    from oracle import oracle
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    d = synth(cfg, 1234, "cpu")
+    if oracle.have_ref():
+        class RefLoss(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, lp, labels, il, ll):
+                costs, grads = oracle.ref_cpu_cost_and_grad(lp.detach().numpy(), labels, il, ll, num_threads=cores)
+                ctx.grads = torch.from_numpy(grads)
+                return torch.from_numpy(costs)
+
+            @staticmethod
+            def backward(ctx, go):
+                return ctx.grads.mul_(go.view(-1, 1, 1, 1)), None, None, None
+
+        def run(n):
+            t0 = time.perf_counter()
+            W, b = d["W"].clone().requires_grad_(), d["b"].clone().requires_grad_()
+            for i in range(n):   # one utterance at a time: the (T,U,V) slab is the only large temporary
+                j = i % B
+                e, p = d["enc"][j:j + 1].clone().requires_grad_(), d["pred"][j:j + 1].clone().requires_grad_()
+                z = torch.tanh(e[:, :, None, :] + p[:, None, :, :])
+                lp = torch.log_softmax(z @ W + b, -1)
+                c = RefLoss.apply(lp, d["labels"][j:j + 1].numpy(), d["il"][j:j + 1].numpy(), d["ll"][j:j + 1].numpy())
+                (c.sum() / B).backward()
+            return time.perf_counter() - t0
+        return run, "reference", cores, "oracle/_ref/libwarprnnt.so (unmodified reference, OpenMP) + torch-CPU fp32 joint/autograd"
+
+    a = {k: v.numpy() for k, v in d.items()}
+
+    def run(n):
+        t0 = time.perf_counter()
+        idx = [i % B for i in range(n)]
+        oracle.joint_loss_grad(a["enc"][idx], a["pred"][idx], a["W"], a["b"], a["labels"][idx], a["il"][idx],
+                               a["ll"][idx], grad_scale=np.full(n, 1.0 / B, np.float32))
+        return time.perf_counter() - t0
+    return run, "port", cores, "oracle/rnnt_oracle.c (C restatement, OpenMP)"
+
+
+def cpu_baseline(cfg, budget_s=20.0):
+    run, kind, cores, note = cpu_reference_runner(cfg)
+    t1 = run(1)                                     # warm-up + calibration
+    n = max(1, min(cfg["B"], int(budget_s / max(t1, 1e-3))))
+    t = run(n)
+    return {"value": n / t, "unit": "utt/s", "cores": cores, "kind": kind,
+            "sample": "%d utterance(s) of the workload shape, %.1f s; %s" % (n, t, note)}
+
+
+def reference_arm(args, cfg, rank):
+    if rank != 0:
+        return
+    run, kind, cores, note = cpu_reference_runner(cfg)
+    t1 = run(1)
+    total = args.steps + args.warmup
+    n = max(1, min(cfg["B"], int(150.0 / (total * max(t1, 1e-3)))))
+    for _ in range(args.warmup):
+        run(n)
+    times = [run(n) for _ in range(args.steps)]
+    tot = sum(times)
+    val = n * args.steps / tot
+    sample = "%d utterance(s) per step; %s" % (n, note)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "utt/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args.gpus, args.workload),
+        "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def workload_config(cfg, n_gpus, name):
+    return {"workload": "BASELINE %s: B=%d T=%d U=%d V=%d H=%d per GPU, joint fwd + alpha/beta + grads (d_enc,d_pred,dW,db)"
+                        % (name.upper(), cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["H"]),
+            "global_batch": cfg["B"] * n_gpus, "parallelism": "dp%d" % n_gpus, "precision": cfg["precision"],
+            "l2": "256 MiB scratch write between timed steps; per-step working set (>4 GB) exceeds the 126 MB L2"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget", type=float, default=20.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    cfg = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, cfg, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import rnnt_speech_recognition_b200 as rb
+    from rnnt_speech_recognition_b200 import _lib, distributed as D
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, T, U, V, H = (cfg[k] for k in "BTUVH")
+    gB = B * world
+    d = synth(cfg, 1234 + rank, dev)
+    host = synth(cfg, 1234 + rank, dev, pin=True)
+    params = [d["W"].clone().requires_grad_(), d["b"].clone().requires_grad_()]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(enc, pred, labels, il, ll):
+        enc.requires_grad_(), pred.requires_grad_()
+        for p in params:
+            p.grad = None
+        costs = rb.joint_rnnt_loss(enc, pred, params[0], params[1], labels, il, ll, precision=cfg["precision"])
+        loss_sum = costs.sum()
+        (loss_sum / gB).backward()                                   # run_rnnt.py:278
+        ls, dW, db = D.allreduce_loss_and_weight_grads(loss_sum.detach(), params[0].grad, params[1].grad)
+        return ls / gB, enc.grad, pred.grad, dW, db
+
+    def resident_step():
+        return step(d["enc"].detach(), d["pred"].detach(), d["labels"], d["il"], d["ll"])
+
+    def e2e_step():
+        dd = {k: host[k].to(dev, non_blocking=True) for k in ("enc", "pred", "labels", "il", "ll")}
+        out = step(dd["enc"], dd["pred"], dd["labels"], dd["il"], dd["ll"])
+        return out[0].item()                                          # D2H read of the step's loss
+
+    def timed(fn, steps):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        for a, b in ev:
+            flush.zero_()                                             # L2 flush, outside the event pair
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)                 # max over ranks
+        return ms.item()
+
+    for _ in range(args.warmup):
+        resident_step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(resident_step, args.steps)
+    launches = _lib.launch_count() - l0
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=3)
+
+    # attribution pass (outside every timed region): per-kernel CUDA-event durations on the launching stream
+    kernels = {}
+    _lib.set_timing(True)
+    resident_step()
+    torch.cuda.synchronize()
+    for name, t in _lib.get_timings():
+        kernels[name] = kernels.get(name, 0.0) + t
+    _lib.set_timing(False)
+
+    if rank == 0:
+        pk, pk_src = peaks()
+        N = B * T * U
+        if cfg["precision"] == "bf16":
+            dom, flops = "joint_tc_kernel<fwd>", 2.0 * N * H * V
+            t_dom = kernels.get(dom)
+            ach = flops / (t_dom * 1e-3) / 1e12 if t_dom else None
+            peak = pk["bf16_tflops_sustained"]
+            roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                    "frac": (ach / peak) if ach else None, "traffic": None,
+                    "peak_source": "%s bf16 sustained (kernel timed inside the step)" % pk_src,
+                    "algorithmic_flops_per_launch": flops, "launch_ms": t_dom,
+                    "step": {"algorithmic_flops": 6.0 * N * H * V,
+                             "achieved": 6.0 * N * H * V / (ms / args.steps * 1e-3) / 1e12,
+                             "frac": 6.0 * N * H * V / (ms / args.steps * 1e-3) / 1e12 / peak}}
+        else:
+            dom = "alpha_beta_kernel"
+            t_dom = kernels.get(dom)
+            byts = 24.0 * N
+            ach = byts / (t_dom * 1e-3) / 1e9 if t_dom else None
+            roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": (ach / pk["hbm_gbs"]) if ach else None, "traffic": None, "peak_source": pk_src,
+                    "algorithmic_bytes_per_launch": byts, "launch_ms": t_dom}
+        h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "pred", "labels", "il", "ll"))
+        out = {
+            "metric": METRIC, "value": gB * args.steps / (ms * 1e-3), "unit": "utt/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": workload_config(cfg, world, args.workload),
+            "clocks": sampler.summary() if sampler else None,
+            "e2e": {"value": gB * args.steps / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches), "roofline": roof,
+            "kernels_ms": {k: round(v, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_budget)
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

