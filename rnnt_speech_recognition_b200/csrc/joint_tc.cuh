@@ -179,34 +179,75 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
         uint32_t g = 0, it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
-            if (!ti.valid) continue;
+            if (!ti.valid) {
+                if (MODE == 1) {  // the plain GEMMs reduce over ALL rows: padding tiles must read as zero
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
+                    for (int i = threadIdx.x; i < 128 * p.V / 8; i += 256) d4[i] = z4;
+                    if (p.zb) {
+                        uint4* z4p = reinterpret_cast<uint4*>(p.zb + (size_t)tile * 128 * p.H);
+                        for (int i = threadIdx.x; i < 128 * p.H / 8; i += 256) z4p[i] = z4;
+                    }
+                }
+                continue;
+            }
             // ---- A operand: z = tanh(enc + pred) -> bf16, SW128 K-major, one 16-byte chunk per thread-task
-            ptx::mbar_wait(z_free, (it & 1) ^ 1);
-            for (int kb = 0; kb < KB; ++kb) {
+            // Per-thread task geometry is fixed for the tile: 4 row-passes x one 16-byte chunk column.
+            uint32_t eo[4], qo[4], soff[4];   // float4-unit offsets into enc / pred, byte offset into a K block
+            bool ok[4];
+            const float4* enc4 = reinterpret_cast<const float4*>(p.enc);
+            const float4* pred4 = reinterpret_cast<const float4*>(p.pred);
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+                const int r = pass * 32 + warp * 4 + (lane >> 3), ch = lane & 7;
+                const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+                ok[pass] = t < ti.Tn && u < ti.Un;
+                eo[pass] = (uint32_t)((((size_t)ti.b * p.maxT + (ok[pass] ? t : 0)) * p.H + ch * 8) >> 2);
+                qo[pass] = (uint32_t)((((size_t)ti.b * p.maxU + (ok[pass] ? u : 0)) * p.H + ch * 8) >> 2);
+                soff[pass] = r * 128 + ((ch ^ (r & 7)) << 4);
+            }
+            // Global loads of K-block kb+1 are issued before the tanh work of K-block kb (two register
+            // buffers, loop unrolled by two) so that their L2 latency overlaps the MUFU work.
+            float4 bufA[16], bufB[16];
+            auto issue = [&](int kb, float4* buf) {
 #pragma unroll
                 for (int pass = 0; pass < 4; ++pass) {
-                    const int r = pass * 32 + warp * 4 + (lane >> 3), ch = lane & 7;
-                    const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+                    const float4* e = enc4 + eo[pass] + kb * 16;   // 64 floats per K block = 16 float4
+                    const float4* q = pred4 + qo[pass] + kb * 16;
+                    buf[pass * 4 + 0] = __ldg(e); buf[pass * 4 + 1] = __ldg(e + 1);
+                    buf[pass * 4 + 2] = __ldg(q); buf[pass * 4 + 3] = __ldg(q + 1);
+                }
+            };
+            auto produce = [&](int kb, const float4* buf) {
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    const float4 e0 = buf[pass * 4], e1 = buf[pass * 4 + 1], q0 = buf[pass * 4 + 2], q1 = buf[pass * 4 + 3];
                     uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                    if (t < ti.Tn && u < ti.Un) {
-                        const int k = kb * 64 + ch * 8;
-                        const float4* e = reinterpret_cast<const float4*>(p.enc + ((size_t)ti.b * p.maxT + t) * p.H + k);
-                        const float4* q = reinterpret_cast<const float4*>(p.pred + ((size_t)ti.b * p.maxU + u) * p.H + k);
-                        const float4 e0 = __ldg(e), e1 = __ldg(e + 1), q0 = __ldg(q), q1 = __ldg(q + 1);
+                    if (ok[pass]) {
                         packed.x = ptx::pack_bf16x2(ptx::tanh_approx(e0.x + q0.x), ptx::tanh_approx(e0.y + q0.y));
                         packed.y = ptx::pack_bf16x2(ptx::tanh_approx(e0.z + q0.z), ptx::tanh_approx(e0.w + q0.w));
                         packed.z = ptx::pack_bf16x2(ptx::tanh_approx(e1.x + q1.x), ptx::tanh_approx(e1.y + q1.y));
                         packed.w = ptx::pack_bf16x2(ptx::tanh_approx(e1.z + q1.z), ptx::tanh_approx(e1.w + q1.w));
                     }
-                    *reinterpret_cast<uint4*>(zs + (size_t)kb * 16384 + r * 128 + ((ch ^ (r & 7)) << 4)) = packed;
+                    *reinterpret_cast<uint4*>(zs + (size_t)kb * 16384 + soff[pass]) = packed;
                     if (MODE == 1 && p.zb) {
-                        const size_t row = ((size_t)(tile)) * 128 + r;
-                        *reinterpret_cast<uint4*>(p.zb + row * p.H + kb * 64 + ch * 8) = packed;
+                        const int r = pass * 32 + warp * 4 + (lane >> 3);
+                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.H + kb * 64 + (lane & 7) * 8) = packed;
                     }
                 }
                 ptx::fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&z_full[kb]);
+            };
+            issue(0, bufA);
+            ptx::mbar_wait(z_free, (it & 1) ^ 1);
+            for (int kb = 0; kb < KB; kb += 2) {
+                if (kb + 1 < KB) issue(kb + 1, bufB);
+                produce(kb, bufA);
+                if (kb + 1 < KB) {
+                    if (kb + 2 < KB) issue(kb + 2, bufA);
+                    produce(kb + 1, bufB);
+                }
             }
             // ---- epilogue: thread = lattice cell (TMEM lane), warps 0-3 cover lanes 0..127
             if (warp < 4) {
@@ -327,42 +368,62 @@ __device__ __forceinline__ float sech2(float x) {
     const float d = 1.f + e;
     return 4.f * e / (d * d);
 }
-struct RowMap { int TT, UU, nTb, nUb, b0; };
+struct RowMap { int TT, UU, nTb, nUb, b0, lgUU; };   // TT*UU == 128, both powers of two
 __device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u) {
-    const size_t q = ((size_t)(b - m.b0) * m.nTb + t / m.TT) * m.nUb + u / m.UU;
-    return q * 128 + (t % m.TT) * m.UU + (u % m.UU);
+    const int lgTT = 7 - m.lgUU;
+    const size_t q = ((size_t)(b - m.b0) * m.nTb + (t >> lgTT)) * m.nUb + (u >> m.lgUU);
+    return q * 128 + ((t & (m.TT - 1)) << m.lgUU) + (u & (m.UU - 1));
 }
-// d_pred[b,u,:] = sum_t g ; grid (ceil(H/128), maxU, nb), block 128 (threads along h)
-__global__ void __launch_bounds__(128) dpred_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
-                                                    const float* __restrict__ pred, const int* __restrict__ xlen,
-                                                    const int* __restrict__ ylen, RowMap m, int maxT, int maxU, int H,
-                                                    float* __restrict__ d_pred) {
-    const int h = blockIdx.x * 128 + threadIdx.x, u = blockIdx.y, b = m.b0 + blockIdx.z;
-    if (h >= H) return;
-    const int Tn = xlen[b], Un = ylen[b] + 1;
-    float acc = 0.f;
-    if (u < Un) {
-        const float pv = pred[((size_t)b * maxU + u) * H + h];
-        for (int t = 0; t < Tn; ++t)
-            acc += dz[tile_row(m, b, t, u) * H + h] * sech2(enc[((size_t)b * maxT + t) * H + h] + pv);
-    }
-    d_pred[((size_t)b * maxU + u) * H + h] = acc;
+inline int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
+// g = dZ * sech^2(enc+pred) reduced over u (d_enc) and over t (d_pred).  Both kernels stream WHOLE rows of
+// dZ (H floats, contiguous): block = H/4 threads x float4, one row per loop iteration, unrolled for memory-level
+// parallelism.  (Two passes over dZ; they disappear once the reduction is fused into the dZ GEMM epilogue.)
+__device__ __forceinline__ float4 g4(const float4 d, const float4 e, const float4 q) {
+    return make_float4(d.x * sech2(e.x + q.x), d.y * sech2(e.y + q.y), d.z * sech2(e.z + q.z), d.w * sech2(e.w + q.w));
 }
-// d_enc[b,t,:] = sum_u g ; grid (ceil(H/128), maxT, nb)
-__global__ void __launch_bounds__(128) denc_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
-                                                   const float* __restrict__ pred, const int* __restrict__ xlen,
-                                                   const int* __restrict__ ylen, RowMap m, int maxT, int maxU, int H,
-                                                   float* __restrict__ d_enc) {
-    const int h = blockIdx.x * 128 + threadIdx.x, t = blockIdx.y, b = m.b0 + blockIdx.z;
-    if (h >= H) return;
+// grid (maxT, nb): d_enc[b,t,:] = sum_u g
+__global__ void __launch_bounds__(256) denc_rows_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+                                                        const float* __restrict__ pred, const int* __restrict__ xlen,
+                                                        const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
+                                                        int H, float* __restrict__ d_enc) {
+    const int t = blockIdx.x, b = m.b0 + blockIdx.y, h4 = threadIdx.x;
+    if (h4 * 4 >= H) return;
     const int Tn = xlen[b], Un = ylen[b] + 1;
-    float acc = 0.f;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (t < Tn) {
-        const float ev = enc[((size_t)b * maxT + t) * H + h];
-        for (int u = 0; u < Un; ++u)
-            acc += dz[tile_row(m, b, t, u) * H + h] * sech2(ev + pred[((size_t)b * maxU + u) * H + h]);
+        const float4 e = reinterpret_cast<const float4*>(enc + ((size_t)b * maxT + t) * H)[h4];
+        const float4* q = reinterpret_cast<const float4*>(pred + (size_t)b * maxU * H) + h4;
+        const int H4 = H >> 2;
+#pragma unroll 8
+        for (int u = 0; u < Un; ++u) {
+            const float4 d = reinterpret_cast<const float4*>(dz + tile_row(m, b, t, u) * H)[h4];
+            const float4 g = g4(d, e, q[(size_t)u * H4]);
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
     }
-    d_enc[((size_t)b * maxT + t) * H + h] = acc;
+    reinterpret_cast<float4*>(d_enc + ((size_t)b * maxT + t) * H)[h4] = acc;
+}
+// grid (maxU, nb): d_pred[b,u,:] = sum_t g
+__global__ void __launch_bounds__(256) dpred_rows_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+                                                         const float* __restrict__ pred, const int* __restrict__ xlen,
+                                                         const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
+                                                         int H, float* __restrict__ d_pred) {
+    const int u = blockIdx.x, b = m.b0 + blockIdx.y, h4 = threadIdx.x;
+    if (h4 * 4 >= H) return;
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (u < Un) {
+        const float4 q = reinterpret_cast<const float4*>(pred + ((size_t)b * maxU + u) * H)[h4];
+        const float4* e = reinterpret_cast<const float4*>(enc + (size_t)b * maxT * H) + h4;
+        const int H4 = H >> 2;
+#pragma unroll 8
+        for (int t = 0; t < Tn; ++t) {
+            const float4 d = reinterpret_cast<const float4*>(dz + tile_row(m, b, t, u) * H)[h4];
+            const float4 g = g4(d, e[(size_t)t * H4], q);
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+    }
+    reinterpret_cast<float4*>(d_pred + ((size_t)b * maxU + u) * H)[h4] = acc;
 }
 // db[v] += sum over VALID tiles' rows of dl[row, v] (bf16 rows); grid (V/64, nsplit), block 256 = 64 cols x 4 row lanes
 __global__ void __launch_bounds__(256) db_kernel(const __nv_bfloat16* __restrict__ dl, const int* __restrict__ xlen,
@@ -536,27 +597,18 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         JointTcParams p;
         tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
         p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb;
-        const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0};
+        const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU)};
         const size_t rows = (size_t)nb * g.nTb * g.nUb * 128;
-        // tiles that lie entirely in the padding are skipped by the kernel; the library GEMMs below reduce
-        // over ALL rows, so those rows must read as zero
-        {
-            ScopedTimer tz("memset(dl,zb)", s);
-            if (cudaMemsetAsync(sc.dl, 0, rows * d.V * 2, s) != cudaSuccess ||
-                cudaMemsetAsync(sc.zb, 0, rows * d.H * 2, s) != cudaSuccess)
-                return RNNT_STATUS_MEMOPS_FAILED;
-        }
         rnntStatus_t st = tc_launch<1>(g, tm, p, s);
         if (st) return st;
         // dZ[rows,H] = dl[rows,V] . Wb[H,V]^T ;  dW[H,V] (+)= zb[rows,H]^T . dl[rows,V]
         st = bwd_gemms(d, g, sc, m, nb, rows, xlen, ylen, dW, /*accumulate=*/b0 > 0, s, launches);
         if (st) return st;
-        ScopedTimer* t1 = new ScopedTimer("dpred_kernel", s);
-        dpred_kernel<<<dim3((d.H + 127) / 128, d.maxU, nb), 128, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT,
-                                                                         d.maxU, d.H, d_pred);
-        delete t1; t1 = new ScopedTimer("denc_kernel", s);
-        denc_kernel<<<dim3((d.H + 127) / 128, d.maxT, nb), 128, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT,
-                                                                        d.maxU, d.H, d_enc);
+        const int rthreads = ((d.H / 4 + 31) / 32) * 32;
+        ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", s);
+        denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
+        delete t1; t1 = new ScopedTimer("dpred_rows_kernel", s);
+        dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_pred);
         delete t1; t1 = new ScopedTimer("db_kernel", s);
         db_kernel<<<dim3(d.V / 64, 64), 256, 0, s>>>(sc.dl, xlen, ylen, m, nb, d.V, db);
         delete t1;
