@@ -20,6 +20,11 @@
 #include <stdint.h>
 
 #include <cstdio>
+#include <cstdlib>
+
+#ifndef RNNTB200_DEFAULT_TC_VARIANT
+#define RNNTB200_DEFAULT_TC_VARIANT 1
+#endif
 
 #include "../../include/rnnt_b200.h"
 #include "kernels_simt.cuh"
@@ -76,6 +81,7 @@ struct JointTcParams {
     int TT, UU, nTb, nUb, NC, NCH, KB, stages;
     long long SK;
     int b0, nb;                 // utterance range of this launch
+    int nbuf, swap, ks, dbg;    // v2 kernel: TMEM accumulator buffers; bf16-pair order of TMEM A; K-blocks per W stage; bring-up switches
     float* lse; float* lpb; float* lpl;              // MODE 0 outputs
     const float4* coef; __nv_bfloat16* dl; __nv_bfloat16* zb;  // MODE 1: coefficients in, dlogits / z rows out
 };
@@ -144,34 +150,37 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
         }
     } else if (warp == 9) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
-            int stage = 0; uint32_t phase = 0, g = 0, it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                if (!decode_tile(p, tile).valid) continue;
-                for (int c = 0; c < NCH; ++c, ++g) {
-                    const uint32_t buf = g & 1;
-                    ptx::mbar_wait(&acc_empty[buf], ((g >> 1) & 1) ^ 1);
+        // whole warp convergent, one elected lane issues (operands stay in uniform registers)
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
+        int stage = 0; uint32_t phase = 0, g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if (!decode_tile(p, tile).valid) continue;
+            for (int c = 0; c < NCH; ++c, ++g) {
+                const uint32_t buf = g & 1;
+                ptx::mbar_wait(&acc_empty[buf], ((g >> 1) & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + buf * NC;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (c == 0) ptx::mbar_wait(&z_full[kb], it & 1);
+                    ptx::mbar_wait(&w_full[stage], phase);
                     ptx::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + buf * NC;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (c == 0) ptx::mbar_wait(&z_full[kb], it & 1);
-                        ptx::mbar_wait(&w_full[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint32_t a0 = ptx::smem_u32(zs + (size_t)kb * 16384);
-                        const uint32_t b0 = ptx::smem_u32(wsm + (size_t)stage * NC * 128);
+                    const uint64_t ad = ptx::umma_desc_k_sw128(ptx::smem_u32(zs + (size_t)kb * 16384));
+                    const uint64_t bd = ptx::umma_desc_k_sw128(ptx::smem_u32(wsm + (size_t)stage * NC * 128));
+                    if (ptx::elect_one()) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16(d_tmem, ptx::umma_desc_k_sw128(a0 + k * 32),
-                                           ptx::umma_desc_k_sw128(b0 + k * 32), idesc, (uint32_t)((kb | k) != 0));
+                            ptx::umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc,
+                                           (uint32_t)((kb | k) != 0));
                         ptx::umma_commit(&w_empty[stage]);
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        if (kb == KB - 1) ptx::umma_commit(&acc_full[buf]);
                     }
-                    ptx::umma_commit(&acc_full[buf]);
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(z_free);
-                ++it;
             }
+            if (ptx::elect_one()) ptx::umma_commit(z_free);
+            __syncwarp();
+            ++it;
         }
     } else {
         // ===================== 8 compute warps: z producers (all) + epilogue (warps 0-3) =====================
@@ -475,6 +484,21 @@ inline bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t rows, uin
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// W^T (V,H) bf16 viewed as 3-D (k within a 64-wide K block, v, K block): one request brings `kblocks` K-major
+// SWIZZLE_128B slabs [box_rows x 64] that land back to back in shared memory.
+inline bool make_tmap_bf16_kblocks(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                                   uint32_t kblocks) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {64, rows, cols / 64};
+    cuuint64_t strides[2] = {cols * 2, 128};
+    cuuint32_t box[3] = {64, box_rows, kblocks};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct TcScratch {
     __nv_bfloat16 *Wt, *Wb, *dl, *zb;
     float* dz;
@@ -547,12 +571,38 @@ inline rnntStatus_t tc_launch(const TcGeom& g, const CUtensorMap& tm, const Join
     return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
 }
 
+// Kernel generation: 1 = z resident in shared memory (joint_tc_kernel), 2 = z resident in tensor memory
+// (joint_tc2_kernel).  RNNTB200_TC_VARIANT overrides the default for A/B measurements.
+inline int tc_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("RNNTB200_TC_VARIANT");
+        v = e ? atoi(e) : RNNTB200_DEFAULT_TC_VARIANT;
+        if (v != 1 && v != 2) v = RNNTB200_DEFAULT_TC_VARIANT;
+    }
+    return v;
+}
+inline int tc_dbg() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_DBG"); v = e ? atoi(e) : 0; }
+    return v;
+}
+inline int tc_swap() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_TC2_SWAP"); v = e ? atoi(e) : 0; }
+    return v;
+}
+
 inline rnntStatus_t tc_unsupported(const rnntb200JointDesc& d) {
     fprintf(stderr,
             "rnnt_b200: RNNTB200_BF16_TC needs H %% 64 == 0, V %% 64 == 0 and H <= 640 for the resident-z kernel "
             "(got H=%d V=%d); use RNNTB200_FP32_EXACT\n", d.H, d.V);
     return RNNT_STATUS_INVALID_VALUE;
 }
+
+template <int MODE>
+inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, const TcScratch& sc, JointTcParams& p,
+                                cudaStream_t s);
 
 inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                const float* W, const float* bias, const int* labels, const int* ylen,
@@ -562,22 +612,38 @@ inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const 
     if (!g.ok) return tc_unsupported(d);
     TcScratch sc = tc_scratch_layout(d, scratch);
     convert_w_kernel<<<dim3((d.V + 31) / 32, (d.H + 31) / 32), 256, 0, s>>>(W, sc.Wt, sc.Wb, d.H, d.V);
-    CUtensorMap tm;
-    if (!make_tmap_bf16(&tm, sc.Wt, d.V, d.H, g.NC)) {
-        fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
-        return RNNT_STATUS_EXECUTION_FAILED;
-    }
     JointTcParams p;
     tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
     p.b0 = 0; p.nb = d.B;
     p.lse = lse; p.lpb = lpb; p.lpl = lpl;
     *launches += 2;
-    return tc_launch<0>(g, tm, p, s);
+    return tc_dispatch<0>(d, g, sc, p, s);
 }
 
 }  // namespace rb
 
 #include "bwd_gemm.cuh"
+#include "joint_tc2.cuh"
+
+namespace rb {
+template <int MODE>
+inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, const TcScratch& sc, JointTcParams& p,
+                                cudaStream_t s) {
+    CUtensorMap tm;
+    const Tc2Geom g2 = tc2_geometry(d.H, d.V);
+    if (tc_variant() == 2 && g2.ok) {
+        if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, TC2_NC, g2.ks)) return RNNT_STATUS_EXECUTION_FAILED;
+        p.NC = TC2_NC; p.NCH = d.V / TC2_NC; p.stages = g2.stages; p.nbuf = g2.nbuf; p.swap = tc_swap(); p.ks = g2.ks;
+        p.dbg = tc_dbg();
+        return tc2_launch<MODE>(g2, tm, p, s);
+    }
+    if (!make_tmap_bf16(&tm, sc.Wt, d.V, d.H, g.NC)) {
+        fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
+        return RNNT_STATUS_EXECUTION_FAILED;
+    }
+    return tc_launch<MODE>(g, tm, p, s);
+}
+}  // namespace rb
 
 namespace rb {
 
@@ -589,8 +655,6 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     if (!g.ok) return tc_unsupported(d);
     TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
-    CUtensorMap tm;
-    if (!make_tmap_bf16(&tm, sc.Wt, d.V, d.H, g.NC)) return RNNT_STATUS_EXECUTION_FAILED;
     if (cudaMemsetAsync(db, 0, sizeof(float) * d.V, s) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
     for (int b0 = 0; b0 < d.B; b0 += sc.bchunk) {
         const int nb = (d.B - b0 < sc.bchunk) ? d.B - b0 : sc.bchunk;
@@ -599,7 +663,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb;
         const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU)};
         const size_t rows = (size_t)nb * g.nTb * g.nUb * 128;
-        rnntStatus_t st = tc_launch<1>(g, tm, p, s);
+        rnntStatus_t st = tc_dispatch<1>(d, g, sc, p, s);
         if (st) return st;
         // dZ[rows,H] = dl[rows,V] . Wb[H,V]^T ;  dW[H,V] (+)= zb[rows,H]^T . dl[rows,V]
         st = bwd_gemms(d, g, sc, m, nb, rows, xlen, ylen, dW, /*accumulate=*/b0 > 0, s, launches);

@@ -23,7 +23,7 @@ constexpr int TC2_NC = 64;
 constexpr int TC2_MAX_STAGES = 24;
 constexpr int TC2_MAX_NBUF = 4;
 
-struct Tc2Geom { int nbuf, stages, zcols; size_t smem_bytes; bool ok; };
+struct Tc2Geom { int nbuf, stages, zcols, ks; size_t smem_bytes; bool ok; };
 inline Tc2Geom tc2_geometry(int H, int V) {
     Tc2Geom g{};
     if (H % 64 || V % 64) return g;
@@ -32,8 +32,16 @@ inline Tc2Geom tc2_geometry(int H, int V) {
     g.nbuf = acc_cols / TC2_NC;
     if (g.nbuf > TC2_MAX_NBUF) g.nbuf = TC2_MAX_NBUF;
     if (g.nbuf < 2) return g;
-    g.stages = TC2_MAX_STAGES;
-    g.smem_bytes = 1024 /*align*/ + 2 * 16384 + (size_t)g.stages * 8192 + 1024 /*barriers*/;
+    // One W stage = ks K-blocks ([64 v x 64 k] boxes, 8 KB each): the MMA thread pays one mbarrier wait and one
+    // commit per 4*ks MMAs.  (With ks = 1 the single issuing thread, not the tensor pipe, set the pace: 123 k
+    // cycles per tile measured on B200.)
+    const int KB = H / 64;
+    g.ks = 1;
+    for (int k = 5; k >= 1; --k)
+        if (KB % k == 0) { g.ks = k; break; }   // largest divisor of KB that is <= 5: stages are never partial
+    g.stages = (int)((size_t)(20 * 8192) / ((size_t)g.ks * 8192));
+    if (g.stages > TC2_MAX_STAGES) g.stages = TC2_MAX_STAGES;
+    g.smem_bytes = 1024 /*align*/ + 2 * 16384 + (size_t)g.stages * g.ks * 8192 + 1024 /*barriers*/;
     g.ok = g.smem_bytes <= 232448;
     return g;
 }
@@ -43,11 +51,12 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                                                                    const JointTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int KB = p.KB, NCH = p.NCH, stages = p.stages, NBUF = p.nbuf;
+    const int KB = p.KB, NCH = p.NCH, stages = p.stages, NBUF = p.nbuf, KS = p.ks;
+    const uint32_t stage_bytes = (uint32_t)KS * 8192u;
     constexpr int NC = TC2_NC;
     uint8_t* sb = smem;                                   // 2 x [128 x 64] bf16 staging tiles (SW128 pattern)
-    uint8_t* wsm = smem + 2 * 16384;                      // stages x [64 x 64] bf16, SW128 K-major (TMA)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * 8192);
+    uint8_t* wsm = smem + 2 * 16384;                      // stages x KS x [64 x 64] bf16, SW128 K-major (TMA)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * stage_bytes);
     uint64_t* z_full = bars;                              // [TC_MAX_KB]      producers -> MMA (K block in TMEM)
     uint64_t* z_free = bars + TC_MAX_KB;                  //                  MMA -> producers
     uint64_t* w_full = z_free + 1;                        // [TC2_MAX_STAGES] TMA -> MMA
@@ -79,45 +88,77 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
             int stage = 0; uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
                 if (!decode_tile(p, tile).valid) continue;
+                if (p.dbg & 4) continue;
                 for (int c = 0; c < NCH; ++c)
-                    for (int kb = 0; kb < KB; ++kb) {
+                    for (int kb0 = 0; kb0 < KB; kb0 += KS) {   // KB % KS == 0: one 3-D box = KS K-block slabs
                         ptx::mbar_wait(&w_empty[stage], phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[stage], 8192u);
-                        ptx::tma_load_2d(wsm + (size_t)stage * 8192, &tmap_wt, &w_full[stage], kb * 64, c * NC);
+                        ptx::mbar_arrive_expect_tx(&w_full[stage], stage_bytes);
+                        ptx::tma_load_3d(wsm + (size_t)stage * stage_bytes, &tmap_wt, &w_full[stage], 0, c * NC, kb0);
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
             }
         }
     } else if (warp == 13) {
         // ===================== MMA issuer: A from TMEM, B from smem =====================
-        if (lane == 0) {
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
-            int stage = 0; uint32_t phase = 0, g = 0, it = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                if (!decode_tile(p, tile).valid) continue;
-                for (int c = 0; c < NCH; ++c, ++g) {
-                    const uint32_t buf = g % NBUF, use = g / NBUF;
-                    ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-                    ptx::tc_fence_after();
-                    const uint32_t d_tmem = acc0 + buf * NC;
-                    for (int kb = 0; kb < KB; ++kb) {
-                        if (c == 0) { ptx::mbar_wait(&z_full[kb], it & 1); }
-                        ptx::mbar_wait(&w_full[stage], phase);
-                        ptx::tc_fence_after();
-                        const uint32_t a0 = tmem_base + (uint32_t)kb * 32;
-                        const uint32_t b0 = ptx::smem_u32(wsm + (size_t)stage * 8192);
+        // The WHOLE warp runs this loop convergently and one elected lane issues: descriptors, TMEM addresses and
+        // barrier addresses then stay in uniform registers.  (Issuing from inside `if (lane == 0)` made every
+        // operand a vector register that had to be moved to the uniform datapath per instruction -- measured
+        // 117 cycles per N=64 MMA instead of the 32-cycle dispatch floor.)
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
+        int stage = 0; uint32_t phase = 0, g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if (!decode_tile(p, tile).valid) continue;
+            for (int c = 0; c < NCH; ++c, ++g) {
+                const uint32_t buf = g % NBUF, use = g / NBUF;
+                ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = acc0 + buf * NC;
+                for (int kb0 = 0; kb0 < KB; kb0 += KS) {
+                    if (!(p.dbg & 4)) ptx::mbar_wait(&w_full[stage], phase);
+                    ptx::tc_fence_after();   // once per stage (4*KS MMAs)
+                    const uint64_t bdesc0 = ptx::umma_desc_k_sw128(ptx::smem_u32(wsm + (size_t)stage * stage_bytes));
+                    const uint32_t a_st = tmem_base + (uint32_t)kb0 * 32;
+                    if (c == 0 && !(p.dbg & 8)) {
+                        // first chunk of a tile: each K block of z must have landed in TMEM before it is read
+                        for (int i = 0; i < KS; ++i) {
+                            ptx::mbar_wait(&z_full[kb0 + i], it & 1);
+                            ptx::tc_fence_after();
+                            if (ptx::elect_one()) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            ptx::umma_bf16_ts(d_tmem, a0 + k * 8, ptx::umma_desc_k_sw128(b0 + k * 32), idesc,
-                                              (uint32_t)((kb | k) != 0));
-                        ptx::umma_commit(&w_empty[stage]);
-                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8, bdesc0 + (uint64_t)(i * 512 + k * 2),
+                                                      idesc, (uint32_t)((kb0 | i | k) != 0));
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        // steady state: the whole stage (up to 20 MMAs) from ONE elected block with immediate
+                        // operand offsets.  A per-K-block loop cost ~40 cycles of issue overhead per 46-cycle MMA.
+                        if (ptx::elect_one()) {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) {
+                                if (i < KS) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8,
+                                                          bdesc0 + (uint64_t)(i * 512 + k * 2), idesc,
+                                                          (i | k) ? 1u : (uint32_t)(kb0 != 0));
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
-                    ptx::umma_commit(&acc_full[buf]);
+                    if (ptx::elect_one()) {
+                        if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
+                        if (kb0 + KS >= KB) ptx::umma_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(z_free);
-                ++it;
             }
+            if (!(p.dbg & 8) && ptx::elect_one()) ptx::umma_commit(z_free);
+            __syncwarp();
+            ++it;
         }
     } else if (warp >= 4) {
         // ===================== producers (warps 4-11, 256 threads) =====================
@@ -125,6 +166,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
         uint32_t it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
+            if (p.dbg & 8) continue;
             if (!ti.valid) {
                 if (MODE == 1) {  // the plain GEMMs reduce over ALL rows: padding tiles must read as zero
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
@@ -150,25 +192,34 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                 qo[pass] = (uint32_t)((((size_t)ti.b * p.maxU + (ok[pass] ? u : 0)) * p.H + ch * 8) >> 2);
                 soff[pass] = r * 128 + ((ch ^ (r & 7)) << 4);
             }
-            float4 bufA[16], bufB[16];
+            // pred rows (distinct per lane group, L2 latency) are prefetched one K block ahead into registers;
+            // enc rows (shared by the whole tile when TT == 1, L1-resident) are loaded just in time.
+            float4 bufA[8], bufB[8];
             auto issue = [&](int kb, float4* buf) {
 #pragma unroll
                 for (int pass = 0; pass < 4; ++pass) {
-                    const float4* e = enc4 + eo[pass] + kb * 16;
                     const float4* q = pred4 + qo[pass] + kb * 16;
-                    buf[pass * 4 + 0] = __ldg(e); buf[pass * 4 + 1] = __ldg(e + 1);
-                    buf[pass * 4 + 2] = __ldg(q); buf[pass * 4 + 3] = __ldg(q + 1);
+                    buf[pass * 2 + 0] = __ldg(q); buf[pass * 2 + 1] = __ldg(q + 1);
                 }
             };
             const int q4 = pw & 3, hh = pw >> 2, r2 = q4 * 32 + lane;   // phase 2: this thread owns TMEM lane r2
             auto produce = [&](int kb, const float4* buf) {
                 uint8_t* stg = sb + (size_t)(kb & 1) * 16384;
+                if (kb + 1 < KB) {   // pull the next K block's enc segment into L1 while this block's tanh work runs
+#pragma unroll
+                    for (int pass = 0; pass < 4; ++pass)
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(enc4 + eo[pass] + (kb + 1) * 16));
+                }
                 // phase 1: tanh -> bf16 -> staging tile (8 lanes cover one row's 64 k: conflict-free 16-byte stores)
 #pragma unroll
                 for (int pass = 0; pass < 4; ++pass) {
-                    const float4 e0 = buf[pass * 4], e1 = buf[pass * 4 + 1], q0 = buf[pass * 4 + 2], q1 = buf[pass * 4 + 3];
+                    const float4* e = enc4 + eo[pass] + kb * 16;
+                    const float4 e0 = __ldg(e), e1 = __ldg(e + 1), q0 = buf[pass * 2], q1 = buf[pass * 2 + 1];
                     uint4 packed = make_uint4(0u, 0u, 0u, 0u);
-                    if (ok[pass]) {
+                    if (ok[pass] && (p.dbg & 2)) {
+                        packed.x = ptx::pack_bf16x2(e0.x + q0.x, e0.y + q0.y); packed.y = ptx::pack_bf16x2(e0.z + q0.z, e0.w + q0.w);
+                        packed.z = ptx::pack_bf16x2(e1.x + q1.x, e1.y + q1.y); packed.w = ptx::pack_bf16x2(e1.z + q1.z, e1.w + q1.w);
+                    } else if (ok[pass]) {
                         packed.x = ptx::pack_bf16x2(ptx::tanh_approx(e0.x + q0.x), ptx::tanh_approx(e0.y + q0.y));
                         packed.y = ptx::pack_bf16x2(ptx::tanh_approx(e0.z + q0.z), ptx::tanh_approx(e0.w + q0.w));
                         packed.z = ptx::pack_bf16x2(ptx::tanh_approx(e1.x + q1.x), ptx::tanh_approx(e1.y + q1.y));
@@ -239,6 +290,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(lane_addr + buf * NC + j * 32, v);
                     ptx::tmem_ld_wait();
+                    if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
                     const int col0 = c * NC + j * 32;
                     const float bv = __ldg(p.bias + col0 + lane) * LOG2E;
                     float y[32];

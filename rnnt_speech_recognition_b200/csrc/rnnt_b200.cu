@@ -13,6 +13,7 @@
 #include "timing.cuh"
 #ifndef RNNTB200_NO_TC
 #include "joint_tc.cuh"
+#include "mma_probe.cuh"
 #endif
 
 namespace {
@@ -391,6 +392,15 @@ rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* e
     }
     return RNNT_STATUS_SUCCESS;
 }
+
+#ifndef RNNTB200_NO_TC
+// bring-up probe (not part of the public header): cycles per tcgen05.mma, see csrc/mma_probe.cuh
+int rnntb200_debug_mma_probe(int variant, int iters, int ctas, float* out_dev) {
+    cudaFuncSetAttribute(rb::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    rb::mma_probe_kernel<<<ctas, 128, 100 * 1024>>>(variant, iters, out_dev);
+    return (int)cudaDeviceSynchronize();
+}
+#endif
 
 unsigned long long rnntb200_launch_count() { return g_launches.load(); }
 
