@@ -279,7 +279,8 @@ def main():
         pk, pk_src = peaks()
         N = B * T * U
         if cfg["precision"] == "bf16":
-            dom, flops = "joint_tc_kernel<fwd>", 2.0 * N * H * V
+            flops = 2.0 * N * H * V
+            dom = next((k for k in kernels if k.endswith("<fwd>")), "joint_tc3_kernel<fwd>")
             t_dom = kernels.get(dom)
             ach = flops / (t_dom * 1e-3) / 1e12 if t_dom else None
             peak = pk["bf16_tflops_sustained"]

@@ -23,7 +23,7 @@
 #include <cstdlib>
 
 #ifndef RNNTB200_DEFAULT_TC_VARIANT
-#define RNNTB200_DEFAULT_TC_VARIANT 1
+#define RNNTB200_DEFAULT_TC_VARIANT 3
 #endif
 
 #include "../../include/rnnt_b200.h"
@@ -499,6 +499,20 @@ inline bool make_tmap_bf16_kblocks(CUtensorMap* tm, const void* base, uint64_t r
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D row-major fp32 matrix [rows x cols], box [box_rows x box_cols]; swizzle128 requires box_cols*4 == 128
+inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                          uint32_t box_cols, bool swizzle128) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {cols * 4};
+    cuuint32_t box[2] = {box_cols, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 struct TcScratch {
     __nv_bfloat16 *Wt, *Wb, *dl, *zb;
     float* dz;
@@ -578,7 +592,7 @@ inline int tc_variant() {
     if (v < 0) {
         const char* e = getenv("RNNTB200_TC_VARIANT");
         v = e ? atoi(e) : RNNTB200_DEFAULT_TC_VARIANT;
-        if (v != 1 && v != 2) v = RNNTB200_DEFAULT_TC_VARIANT;
+        if (v < 1 || v > 3) v = RNNTB200_DEFAULT_TC_VARIANT;
     }
     return v;
 }
@@ -624,6 +638,7 @@ inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const 
 
 #include "bwd_gemm.cuh"
 #include "joint_tc2.cuh"
+#include "joint_tc3.cuh"
 
 namespace rb {
 template <int MODE>
@@ -631,6 +646,17 @@ inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, con
                                 cudaStream_t s) {
     CUtensorMap tm;
     const Tc2Geom g2 = tc2_geometry(d.H, d.V);
+    const Tc2Geom g3 = tc3_geometry(d.H, d.V);
+    if (tc_variant() == 3 && g3.ok) {
+        CUtensorMap tmp, tme;
+        if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, TC2_NC, g3.ks) ||
+            !make_tmap_f32(&tmp, p.pred, (uint64_t)d.B * d.maxU, d.H, g.UU, 32, true) ||
+            !make_tmap_f32(&tme, p.enc, (uint64_t)d.B * d.maxT, d.H, g.TT, 64, false))
+            return RNNT_STATUS_EXECUTION_FAILED;
+        p.NC = TC2_NC; p.NCH = d.V / TC2_NC; p.stages = g3.stages; p.nbuf = g3.nbuf; p.swap = 0; p.ks = g3.ks;
+        p.dbg = tc_dbg();
+        return tc3_launch<MODE>(g3, tm, tmp, tme, p, s);
+    }
     if (tc_variant() == 2 && g2.ok) {
         if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, TC2_NC, g2.ks)) return RNNT_STATUS_EXECUTION_FAILED;
         p.NC = TC2_NC; p.NCH = d.V / TC2_NC; p.stages = g2.stages; p.nbuf = g2.nbuf; p.swap = tc_swap(); p.ks = g2.ks;

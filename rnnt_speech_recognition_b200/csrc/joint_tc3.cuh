@@ -1,0 +1,338 @@
+// joint_tc3.cuh -- third-generation fused joint kernel = joint_tc2 (z resident in TENSOR MEMORY, deep W ring,
+// whole-stage MMA issue) + TMA-fed producers.
+//
+// v2's producers (coalesced global loads -> tanh -> smem staging -> 256-thread barrier -> re-read own row ->
+// tcgen05.st) took ~2.1 k cycles per K block, and because z is single-buffered in TMEM that chain gates the first
+// V-chunk of every tile (measured: 1.2 ms of a 3.8 ms kernel).  Here a dedicated warp TMA-loads the tile's
+// pred rows (box [32 fp32 x UU rows], SWIZZLE_128B) and enc rows (box [64 x TT]) K block by K block into a
+// ring, RUNNING AHEAD across tiles; each producer thread then reads ITS OWN lattice row straight from shared
+// memory (conflict-free), applies tanh, packs to bf16 and writes its TMEM lane with tcgen05.st -- no staging
+// pass, no inter-warp barrier, no register prefetch buffers.
+//
+// Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
+#pragma once
+#include "joint_tc2.cuh"
+
+namespace rb {
+
+constexpr int TC3_THREADS = 480;
+constexpr int TC3_IN_STAGES = 2;
+
+inline Tc2Geom tc3_geometry(int H, int V) {
+    Tc2Geom g = tc2_geometry(H, V);
+    if (!g.ok) return g;
+    // smem: enc/pred ring (2 x (2 x 16 KB pred boxes + 4 KB enc box)) + W ring; W stages shrink to fit
+    const size_t in_bytes = (size_t)TC3_IN_STAGES * (2 * 16384 + 4096);
+    const size_t budget = 232448 - 1024 - 1024 - in_bytes;
+    g.stages = (int)(budget / ((size_t)g.ks * 8192));
+    if (g.stages > 6) g.stages = 6;
+    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024;
+    g.ok = g.stages >= 2;
+    return g;
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_constant__ CUtensorMap tmap_wt,
+                                                                   const __grid_constant__ CUtensorMap tmap_pred,
+                                                                   const __grid_constant__ CUtensorMap tmap_enc,
+                                                                   const JointTcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const int KB = p.KB, NCH = p.NCH, stages = p.stages, NBUF = p.nbuf, KS = p.ks;
+    const uint32_t stage_bytes = (uint32_t)KS * 8192u;
+    constexpr int NC = TC2_NC;
+    uint8_t* insm = smem;                                 // TC3_IN_STAGES x {pred box k-half 0, k-half 1 (16 KB each, SW128), enc box (4 KB)}
+    constexpr uint32_t IN_STAGE = 2 * 16384 + 4096;
+    uint8_t* wsm = smem + TC3_IN_STAGES * IN_STAGE;       // stages x KS x [64 x 64] bf16, SW128 K-major (TMA)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * stage_bytes);
+    uint64_t* z_full = bars;                              // [TC_MAX_KB]      producers -> MMA (K block in TMEM)
+    uint64_t* z_free = bars + TC_MAX_KB;                  //                  MMA -> producers
+    uint64_t* w_full = z_free + 1;                        // [TC2_MAX_STAGES] TMA -> MMA
+    uint64_t* w_empty = w_full + TC2_MAX_STAGES;          // [TC2_MAX_STAGES] MMA -> TMA
+    uint64_t* acc_full = w_empty + TC2_MAX_STAGES;        // [TC2_MAX_NBUF]   MMA -> epilogue
+    uint64_t* acc_empty = acc_full + TC2_MAX_NBUF;        // [TC2_MAX_NBUF]   epilogue -> MMA
+    uint64_t* in_full = acc_empty + TC2_MAX_NBUF;         // [TC3_IN_STAGES]  input TMA -> producers
+    uint64_t* in_empty = in_full + TC3_IN_STAGES;         // [TC3_IN_STAGES]  producers -> input TMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + TC3_IN_STAGES);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < TC_MAX_KB; ++i) ptx::mbar_init(&z_full[i], 8);
+        ptx::mbar_init(z_free, 1);
+        for (int i = 0; i < TC2_MAX_STAGES; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
+        for (int i = 0; i < TC2_MAX_NBUF; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < TC3_IN_STAGES; ++i) { ptx::mbar_init(&in_full[i], 1); ptx::mbar_init(&in_empty[i], 8); }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 13) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp == 12 && lane == 0) ptx::prefetch_tmap(&tmap_wt);
+    if (warp == 14 && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const uint32_t acc0 = tmem_base + (uint32_t)KB * 32;  // accumulator region starts after the z columns
+    const int ntiles = p.nb * p.nTb * p.nUb;
+
+    if (warp == 14) {
+        // ===================== enc / pred TMA: one K block of the tile's rows per ring stage, runs ahead across tiles
+        if (lane == 0 && !(p.dbg & 8)) {
+            int st = 0; uint32_t ph = 0;
+            const uint32_t tx = 2u * (uint32_t)p.UU * 128u + (uint32_t)p.TT * 256u;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                const TileInfo ti = decode_tile(p, tile);
+                if (!ti.valid) continue;
+                for (int kb = 0; kb < KB; ++kb) {
+                    ptx::mbar_wait(&in_empty[st], ph ^ 1);
+                    ptx::mbar_arrive_expect_tx(&in_full[st], tx);
+                    uint8_t* base = insm + (size_t)st * IN_STAGE;
+                    ptx::tma_load_2d(base, &tmap_pred, &in_full[st], kb * 64, ti.b * p.maxU + ti.u0);
+                    ptx::tma_load_2d(base + 16384, &tmap_pred, &in_full[st], kb * 64 + 32, ti.b * p.maxU + ti.u0);
+                    ptx::tma_load_2d(base + 32768, &tmap_enc, &in_full[st], kb * 64, ti.b * p.maxT + ti.t0);
+                    if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 12) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+                if (!decode_tile(p, tile).valid) continue;
+                if (p.dbg & 4) continue;
+                for (int c = 0; c < NCH; ++c)
+                    for (int kb0 = 0; kb0 < KB; kb0 += KS) {   // KB % KS == 0: one 3-D box = KS K-block slabs
+                        ptx::mbar_wait(&w_empty[stage], phase ^ 1);
+                        ptx::mbar_arrive_expect_tx(&w_full[stage], stage_bytes);
+                        ptx::tma_load_3d(wsm + (size_t)stage * stage_bytes, &tmap_wt, &w_full[stage], 0, c * NC, kb0);
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == 13) {
+        // ===================== MMA issuer: A from TMEM, B from smem =====================
+        // The WHOLE warp runs this loop convergently and one elected lane issues: descriptors, TMEM addresses and
+        // barrier addresses then stay in uniform registers.  (Issuing from inside `if (lane == 0)` made every
+        // operand a vector register that had to be moved to the uniform datapath per instruction -- measured
+        // 117 cycles per N=64 MMA instead of the 32-cycle dispatch floor.)
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
+        int stage = 0; uint32_t phase = 0, g = 0, it = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            if (!decode_tile(p, tile).valid) continue;
+            for (int c = 0; c < NCH; ++c, ++g) {
+                const uint32_t buf = g % NBUF, use = g / NBUF;
+                ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = acc0 + buf * NC;
+                for (int kb0 = 0; kb0 < KB; kb0 += KS) {
+                    if (!(p.dbg & 4)) ptx::mbar_wait(&w_full[stage], phase);
+                    ptx::tc_fence_after();   // once per stage (4*KS MMAs)
+                    const uint64_t bdesc0 = ptx::umma_desc_k_sw128(ptx::smem_u32(wsm + (size_t)stage * stage_bytes));
+                    const uint32_t a_st = tmem_base + (uint32_t)kb0 * 32;
+                    if (c == 0 && !(p.dbg & 8)) {
+                        // first chunk of a tile: each K block of z must have landed in TMEM before it is read
+                        for (int i = 0; i < KS; ++i) {
+                            ptx::mbar_wait(&z_full[kb0 + i], it & 1);
+                            ptx::tc_fence_after();
+                            if (ptx::elect_one()) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8, bdesc0 + (uint64_t)(i * 512 + k * 2),
+                                                      idesc, (uint32_t)((kb0 | i | k) != 0));
+                            }
+                            __syncwarp();
+                        }
+                    } else {
+                        // steady state: the whole stage (up to 20 MMAs) from ONE elected block with immediate
+                        // operand offsets.  A per-K-block loop cost ~40 cycles of issue overhead per 46-cycle MMA.
+                        if (ptx::elect_one()) {
+#pragma unroll
+                            for (int i = 0; i < 5; ++i) {
+                                if (i < KS) {
+#pragma unroll
+                                    for (int k = 0; k < 4; ++k)
+                                        ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8,
+                                                          bdesc0 + (uint64_t)(i * 512 + k * 2), idesc,
+                                                          (i | k) ? 1u : (uint32_t)(kb0 != 0));
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                    if (ptx::elect_one()) {
+                        if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
+                        if (kb0 + KS >= KB) ptx::umma_commit(&acc_full[buf]);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (!(p.dbg & 8) && ptx::elect_one()) ptx::umma_commit(z_free);
+            __syncwarp();
+            ++it;
+        }
+    } else if (warp >= 4 && warp < 12) {
+        // ===================== producers (warps 4-11): thread = (lattice row r2 = TMEM lane, k-half hh) =====================
+        const int pw = warp - 4, ptid = threadIdx.x - 128;
+        const int q4 = pw & 3, hh = pw >> 2, r2 = q4 * 32 + lane;
+        uint32_t it = 0; int st = 0; uint32_t ph = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const TileInfo ti = decode_tile(p, tile);
+            if (p.dbg & 8) continue;
+            if (!ti.valid) {
+                if (MODE == 1) {  // the plain GEMMs reduce over ALL rows: padding tiles must read as zero
+                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                    uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
+                    for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
+                    if (p.zb) {
+                        uint4* z4p = reinterpret_cast<uint4*>(p.zb + (size_t)tile * 128 * p.H);
+                        for (int i = ptid; i < 128 * p.H / 8; i += 256) z4p[i] = z4;
+                    }
+                }
+                continue;
+            }
+            const int tl = r2 / p.UU, ul = r2 % p.UU;   // row of the enc box / of the pred box
+            const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
+            for (int kb = 0; kb < KB; ++kb) {
+                ptx::mbar_wait(&in_full[st], ph);
+                const uint8_t* base = insm + (size_t)st * IN_STAGE;
+                const uint8_t* prow = base + (size_t)hh * 16384 + ul * 128;          // SW128: chunk c at (c ^ (row & 7)) * 16
+                const uint8_t* erow = base + 32768 + tl * 256 + hh * 128;            // plain layout
+                uint32_t zr[16];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 q = *reinterpret_cast<const float4*>(prow + ((c ^ (ul & 7)) << 4));
+                    const float4 e = *reinterpret_cast<const float4*>(erow + (c << 4));
+                    if (ok) {
+                        zr[c * 2 + 0] = ptx::pack_bf16x2(ptx::tanh_approx(e.x + q.x), ptx::tanh_approx(e.y + q.y));
+                        zr[c * 2 + 1] = ptx::pack_bf16x2(ptx::tanh_approx(e.z + q.z), ptx::tanh_approx(e.w + q.w));
+                    } else {
+                        zr[c * 2 + 0] = 0u; zr[c * 2 + 1] = 0u;
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
+                if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
+                if (MODE == 1 && p.zb) {
+                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r2) * p.H + kb * 64 + hh * 32);
+                    zdst[0] = make_uint4(zr[0], zr[1], zr[2], zr[3]);   zdst[1] = make_uint4(zr[4], zr[5], zr[6], zr[7]);
+                    zdst[2] = make_uint4(zr[8], zr[9], zr[10], zr[11]); zdst[3] = make_uint4(zr[12], zr[13], zr[14], zr[15]);
+                }
+                if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);   // previous tile's MMAs have retired: z columns reusable
+                ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zr);
+                ptx::tmem_st_wait();
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&z_full[kb]);
+            }
+            ++it;
+        }
+    } else if (warp < 4) {
+        // ===================== epilogue warps 0-3: thread = lattice cell (TMEM lane) =====================
+        constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        uint32_t g = 0;
+        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const TileInfo ti = decode_tile(p, tile);
+            if (!ti.valid) continue;
+            const int r = warp * 32 + lane;
+            const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+            const bool rv = t < ti.Tn && u < ti.Un;
+            const int lab = (rv && u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
+            const long long cell = ((long long)ti.b * p.maxT + t) * p.maxU + u;
+            float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f;
+            float kd2 = -CUDART_INF_F, cg = 0.f, csb = 0.f, csl = 0.f;
+            if (MODE == 1 && rv) {
+                const float4 cf = p.coef[cell];
+                kd2 = cf.x * LOG2E; cg = cf.y; csb = cf.z; csl = cf.w;
+            }
+            const uint32_t lane_addr = acc0 + ((uint32_t)(warp * 32) << 16);
+            for (int c = 0; c < NCH; ++c, ++g) {
+                const uint32_t buf = g % NBUF, use = g / NBUF;
+                ptx::mbar_wait(&acc_full[buf], use & 1);
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < NC / 32; ++j) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(lane_addr + buf * NC + j * 32, v);
+                    ptx::tmem_ld_wait();
+                    if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
+                    const int col0 = c * NC + j * 32;
+                    const float bv = __ldg(p.bias + col0 + lane) * LOG2E;
+                    float y[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
+                    if (MODE == 0) {
+                        float gm = y[0];
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
+                        const float mn = fmaxf(m2, gm);
+                        float acc = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) acc += ptx::ex2_approx(y[i] - mn);
+                        s = s * ptx::ex2_approx(m2 - mn) + acc;
+                        m2 = mn;
+                        if (p.blank >= col0 && p.blank < col0 + 32) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (col0 + i == p.blank) yb = y[i];
+                        }
+                        const int d = lab - col0;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) yl = (i == d) ? y[i] : yl;
+                    } else {
+                        const int d = lab - col0, db = p.blank - col0;
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) {
+                            float d0 = cg * ptx::ex2_approx(y[i] + kd2);
+                            float d1 = cg * ptx::ex2_approx(y[i + 1] + kd2);
+                            if (i == db) d0 -= csb;
+                            if (i + 1 == db) d1 -= csb;
+                            if (i == d) d0 -= csl;
+                            if (i + 1 == d) d1 -= csl;
+                            o[i >> 1] = ptx::pack_bf16x2(d0, d1);
+                        }
+                        uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
+                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                    }
+                }
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+            }
+            if (MODE == 0 && rv) {
+                const float lse2 = m2 + log2f(s);
+                p.lse[cell] = lse2 * LN2;
+                const long long k = sk_index(ti.b, t, u, p.maxU, p.SK);
+                p.lpb[k] = (yb - lse2) * LN2;
+                if (u < ti.Un - 1) p.lpl[k] = (yl - lse2) * LN2;
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 13) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+template <int MODE>
+inline rnntStatus_t tc3_launch(const Tc2Geom& g3, const CUtensorMap& tm, const CUtensorMap& tmp, const CUtensorMap& tme,
+                               const JointTcParams& p, cudaStream_t s) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(joint_tc3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)232448) != cudaSuccess)
+            return RNNT_STATUS_EXECUTION_FAILED;
+        attr_set = true;
+    }
+    const int ntiles = p.nb * p.nTb * p.nUb;
+    const int grid = ntiles < tc_num_sms() ? ntiles : tc_num_sms();
+    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : "joint_tc3_kernel<dlogits>", s);
+    joint_tc3_kernel<MODE><<<grid, TC3_THREADS, g3.smem_bytes, s>>>(tm, tmp, tme, p);
+    return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
+}
+
+}  // namespace rb
