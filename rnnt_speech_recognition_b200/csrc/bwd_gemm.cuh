@@ -1,6 +1,7 @@
 // bwd_gemm.cuh -- the two plain GEMMs of the bf16 backward over the materialised bf16 dlogits rows:
-//     dZ[rows,H]  = dl[rows,V] . Wb[H,V]^T          (fp32 out)
-//     dW[H,V]    (+)= zb[rows,H]^T . dl[rows,V]     (fp32 out, accumulated across utterance chunks)
+//     dZ[rows,H]    = dl[rows,V] . Wb[H,V]^T            (bf16 out: halves the traffic of the two reduction passes)
+//     dWx[H+8,V] (+)= zb[rows,H+8]^T . dl[rows,V]       (fp32 out, accumulated across utterance chunks; zb carries a
+//                                                        ones column at index H, so row H of dWx is db = sum_rows dl)
 // RNNTB200_BWD_CUBLAS: interim library path (cuBLAS is allowed for PLAIN GEMMs; these two have no
 // fused prologue/epilogue).  It is the baseline the hand-written tcgen05 kernels are checked against.
 #pragma once
@@ -24,13 +25,14 @@ inline rnntStatus_t bwd_gemms(const rnntb200JointDesc& d, const TcGeom& g, const
     ScopedTimer* t = new ScopedTimer("gemm dZ=dl.W^T (cublas)", s);
     // row-major dZ[rows,H] == column-major [H,rows] = Wb_cm[V,H]^T . dl_cm[V,rows]
     if (cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, d.H, (int)rows, d.V, &one, sc.Wb, CUDA_R_16BF, d.V, sc.dl,
-                     CUDA_R_16BF, d.V, &zero, sc.dz, CUDA_R_32F, d.H, CUBLAS_COMPUTE_32F,
+                     CUDA_R_16BF, d.V, &zero, sc.dz, CUDA_R_16BF, d.H, CUBLAS_COMPUTE_32F,
                      CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
         return RNNT_STATUS_EXECUTION_FAILED;
     delete t; t = new ScopedTimer("gemm dW=z^T.dl (cublas)", s);
-    // row-major dW[H,V] == column-major [V,H] = dl_cm[V,rows] . zb_cm[H,rows]^T
-    if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, d.V, d.H, (int)rows, &one, sc.dl, CUDA_R_16BF, d.V, sc.zb,
-                     CUDA_R_16BF, d.H, &beta, dW, CUDA_R_32F, d.V, CUBLAS_COMPUTE_32F,
+    // row-major dWx[H+8,V] == column-major [V,H+8] = dl_cm[V,rows] . zb_cm[H+8,rows]^T
+    (void)dW;
+    if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, d.V, d.H + 8, (int)rows, &one, sc.dl, CUDA_R_16BF, d.V, sc.zb,
+                     CUDA_R_16BF, d.H + 8, &beta, sc.dWx, CUDA_R_32F, d.V, CUBLAS_COMPUTE_32F,
                      CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
         return RNNT_STATUS_EXECUTION_FAILED;
     delete t;

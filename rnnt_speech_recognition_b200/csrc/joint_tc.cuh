@@ -81,6 +81,7 @@ struct JointTcParams {
     int TT, UU, nTb, nUb, NC, NCH, KB, stages;
     long long SK;
     int b0, nb;                 // utterance range of this launch
+    int zld;                    // row stride (elements) of zb: H + 8 (the extra 8 columns carry the ones column for db)
     int nbuf, swap, ks, dbg;    // v2 kernel: TMEM accumulator buffers; bf16-pair order of TMEM A; K-blocks per W stage; bring-up switches
     float* lse; float* lpb; float* lpl;              // MODE 0 outputs
     const float4* coef; __nv_bfloat16* dl; __nv_bfloat16* zb;  // MODE 1: coefficients in, dlogits / z rows out
@@ -194,8 +195,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                     uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
                     for (int i = threadIdx.x; i < 128 * p.V / 8; i += 256) d4[i] = z4;
                     if (p.zb) {
-                        uint4* z4p = reinterpret_cast<uint4*>(p.zb + (size_t)tile * 128 * p.H);
-                        for (int i = threadIdx.x; i < 128 * p.H / 8; i += 256) z4p[i] = z4;
+                        const int h8 = p.H / 8;
+                        for (int i = threadIdx.x; i < 128 * h8; i += 256)
+                            *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + i / h8) * p.zld + (i % h8) * 8) = z4;
                     }
                 }
                 continue;
@@ -241,7 +243,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                     *reinterpret_cast<uint4*>(zs + (size_t)kb * 16384 + soff[pass]) = packed;
                     if (MODE == 1 && p.zb) {
                         const int r = pass * 32 + warp * 4 + (lane >> 3);
-                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.H + kb * 64 + (lane & 7) * 8) = packed;
+                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.zld + kb * 64 + (lane & 7) * 8) = packed;
                     }
                 }
                 ptx::fence_proxy_async_smem();
@@ -374,8 +376,8 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float sech2(float x) {
     const float e = ptx::ex2_approx(-2.8853900817779268f * fabsf(x));  // exp(-2|x|)
-    const float d = 1.f + e;
-    return 4.f * e / (d * d);
+    const float r = __frcp_rn(1.f + e);                                   // 1+e in [1,2]: one Newton-free reciprocal
+    return 4.f * e * r * r;
 }
 struct RowMap { int TT, UU, nTb, nUb, b0, lgUU; };   // TT*UU == 128, both powers of two
 __device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u) {
@@ -384,75 +386,78 @@ __device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u)
     return q * 128 + ((t & (m.TT - 1)) << m.lgUU) + (u & (m.UU - 1));
 }
 inline int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
-// g = dZ * sech^2(enc+pred) reduced over u (d_enc) and over t (d_pred).  Both kernels stream WHOLE rows of
-// dZ (H floats, contiguous): block = H/4 threads x float4, one row per loop iteration, unrolled for memory-level
-// parallelism.  (Two passes over dZ; they disappear once the reduction is fused into the dZ GEMM epilogue.)
-__device__ __forceinline__ float4 g4(const float4 d, const float4 e, const float4 q) {
-    return make_float4(d.x * sech2(e.x + q.x), d.y * sech2(e.y + q.y), d.z * sech2(e.z + q.z), d.w * sech2(e.w + q.w));
+// g = dZ * sech^2(enc+pred) reduced over u (d_enc) and over t (d_pred).  Both kernels stream WHOLE rows of the
+// bf16 dZ (H elements, contiguous): block = H/8 threads x 16-byte loads, one row per loop iteration, unrolled for
+// memory-level parallelism.
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 load_bf16x8(const __nv_bfloat16* p) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    F8 o;
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { o.v[2 * i] = __uint_as_float(w[i] << 16); o.v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+    return o;
+}
+__device__ __forceinline__ F8 load_f32x8(const float* p) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    F8 o; o.v[0] = a.x; o.v[1] = a.y; o.v[2] = a.z; o.v[3] = a.w; o.v[4] = b.x; o.v[5] = b.y; o.v[6] = b.z; o.v[7] = b.w;
+    return o;
+}
+__device__ __forceinline__ void store_f32x8(float* p, const F8& a) {
+    *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
+    *reinterpret_cast<float4*>(p + 4) = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
 }
 // grid (maxT, nb): d_enc[b,t,:] = sum_u g
-__global__ void __launch_bounds__(256) denc_rows_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+__global__ void __launch_bounds__(128) denc_rows_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ enc,
                                                         const float* __restrict__ pred, const int* __restrict__ xlen,
                                                         const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
                                                         int H, float* __restrict__ d_enc) {
-    const int t = blockIdx.x, b = m.b0 + blockIdx.y, h4 = threadIdx.x;
-    if (h4 * 4 >= H) return;
+    const int t = blockIdx.x, b = m.b0 + blockIdx.y, h = threadIdx.x * 8;
+    if (h >= H) return;
     const int Tn = xlen[b], Un = ylen[b] + 1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    F8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
     if (t < Tn) {
-        const float4 e = reinterpret_cast<const float4*>(enc + ((size_t)b * maxT + t) * H)[h4];
-        const float4* q = reinterpret_cast<const float4*>(pred + (size_t)b * maxU * H) + h4;
-        const int H4 = H >> 2;
-#pragma unroll 8
+        const F8 e = load_f32x8(enc + ((size_t)b * maxT + t) * H + h);
+#pragma unroll 4
         for (int u = 0; u < Un; ++u) {
-            const float4 d = reinterpret_cast<const float4*>(dz + tile_row(m, b, t, u) * H)[h4];
-            const float4 g = g4(d, e, q[(size_t)u * H4]);
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            const F8 d = load_bf16x8(dz + tile_row(m, b, t, u) * H + h);
+            const F8 q = load_f32x8(pred + ((size_t)b * maxU + u) * H + h);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc.v[i] += d.v[i] * sech2(e.v[i] + q.v[i]);
         }
     }
-    reinterpret_cast<float4*>(d_enc + ((size_t)b * maxT + t) * H)[h4] = acc;
+    store_f32x8(d_enc + ((size_t)b * maxT + t) * H + h, acc);
 }
 // grid (maxU, nb): d_pred[b,u,:] = sum_t g
-__global__ void __launch_bounds__(256) dpred_rows_kernel(const float* __restrict__ dz, const float* __restrict__ enc,
+__global__ void __launch_bounds__(128) dpred_rows_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ enc,
                                                          const float* __restrict__ pred, const int* __restrict__ xlen,
                                                          const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
                                                          int H, float* __restrict__ d_pred) {
-    const int u = blockIdx.x, b = m.b0 + blockIdx.y, h4 = threadIdx.x;
-    if (h4 * 4 >= H) return;
+    const int u = blockIdx.x, b = m.b0 + blockIdx.y, h = threadIdx.x * 8;
+    if (h >= H) return;
     const int Tn = xlen[b], Un = ylen[b] + 1;
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    F8 acc;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
     if (u < Un) {
-        const float4 q = reinterpret_cast<const float4*>(pred + ((size_t)b * maxU + u) * H)[h4];
-        const float4* e = reinterpret_cast<const float4*>(enc + (size_t)b * maxT * H) + h4;
-        const int H4 = H >> 2;
-#pragma unroll 8
+        const F8 q = load_f32x8(pred + ((size_t)b * maxU + u) * H + h);
+#pragma unroll 4
         for (int t = 0; t < Tn; ++t) {
-            const float4 d = reinterpret_cast<const float4*>(dz + tile_row(m, b, t, u) * H)[h4];
-            const float4 g = g4(d, e[(size_t)t * H4], q);
-            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+            const F8 d = load_bf16x8(dz + tile_row(m, b, t, u) * H + h);
+            const F8 e = load_f32x8(enc + ((size_t)b * maxT + t) * H + h);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc.v[i] += d.v[i] * sech2(e.v[i] + q.v[i]);
         }
     }
-    reinterpret_cast<float4*>(d_pred + ((size_t)b * maxU + u) * H)[h4] = acc;
+    store_f32x8(d_pred + ((size_t)b * maxU + u) * H + h, acc);
 }
-// db[v] += sum over VALID tiles' rows of dl[row, v] (bf16 rows); grid (V/64, nsplit), block 256 = 64 cols x 4 row lanes
-__global__ void __launch_bounds__(256) db_kernel(const __nv_bfloat16* __restrict__ dl, const int* __restrict__ xlen,
-                                                 const int* __restrict__ ylen, RowMap m, int nb, int V,
-                                                 float* __restrict__ db) {
-    const int v = blockIdx.x * 64 + (threadIdx.x & 63), rl = threadIdx.x >> 6;
-    const int ntiles = nb * m.nTb * m.nUb, per_utt = m.nTb * m.nUb;
-    float acc = 0.f;
-    for (int tile = blockIdx.y; tile < ntiles; tile += gridDim.y) {
-        const int bl = tile / per_utt, rem = tile - bl * per_utt, b = m.b0 + bl;
-        if ((rem / m.nUb) * m.TT >= xlen[b] || (rem % m.nUb) * m.UU >= ylen[b] + 1) continue;  // tile never written
-        const __nv_bfloat16* base = dl + (size_t)tile * 128 * V + v;
-        for (int r = rl; r < 128; r += 4) acc += __bfloat162float(base[(size_t)r * V]);
-    }
-    __shared__ float sm[4][64];
-    sm[rl][threadIdx.x & 63] = acc;
-    __syncthreads();
-    if (rl == 0) atomicAdd(db + v, sm[0][v & 63] + sm[1][v & 63] + sm[2][v & 63] + sm[3][v & 63]);
+// zb[row, H .. H+7] = (1, 0, ..., 0): the ones column that turns the dW GEMM's extra output row into db
+__global__ void __launch_bounds__(256) zb_ones_kernel(__nv_bfloat16* __restrict__ zb, size_t rows, int H, int zld) {
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < rows) *reinterpret_cast<uint4*>(zb + r * zld + H) = make_uint4(0x00003F80u, 0u, 0u, 0u);   // bf16(1.0) = 0x3F80
 }
-
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -514,8 +519,8 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 }
 
 struct TcScratch {
-    __nv_bfloat16 *Wt, *Wb, *dl, *zb;
-    float* dz;
+    __nv_bfloat16 *Wt, *Wb, *dl, *zb, *dz;   // zb rows have stride H+8 (ones column at H); dz is bf16
+    float* dWx;                             // (H+8, V) fp32: dW rows, then the db row produced by the ones column
     int bchunk;          // utterances per backward pass
     size_t rows_chunk;   // bchunk * tiles_per_utt * 128
     size_t bytes;
@@ -524,7 +529,7 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     TcScratch s{};
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
-    const size_t per_row = (size_t)d.V * 2 + (size_t)d.H * 2 + (size_t)d.H * 4;
+    const size_t per_row = (size_t)d.V * 2 + (size_t)(d.H + 8) * 2 + (size_t)d.H * 2;
     const size_t budget = (size_t)16 << 30;
     size_t bc = budget / (rows_utt * per_row);
     if (bc < 1) bc = 1;
@@ -536,8 +541,9 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.Wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.dl = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.V * 2));
-    s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
-    s.dz = reinterpret_cast<float*>(take(s.rows_chunk * d.H * 4));
+    s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * (d.H + 8) * 2));
+    s.dz = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
+    s.dWx = reinterpret_cast<float*>(take((size_t)(d.H + 8) * d.V * 4));
     s.bytes = (size_t)(p - static_cast<char*>(base));
     return s;
 }
@@ -681,30 +687,31 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     if (!g.ok) return tc_unsupported(d);
     TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
-    if (cudaMemsetAsync(db, 0, sizeof(float) * d.V, s) != cudaSuccess) return RNNT_STATUS_MEMOPS_FAILED;
     for (int b0 = 0; b0 < d.B; b0 += sc.bchunk) {
         const int nb = (d.B - b0 < sc.bchunk) ? d.B - b0 : sc.bchunk;
         JointTcParams p;
         tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
-        p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb;
+        p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb; p.zld = d.H + 8;
         const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU)};
         const size_t rows = (size_t)nb * g.nTb * g.nUb * 128;
         rnntStatus_t st = tc_dispatch<1>(d, g, sc, p, s);
         if (st) return st;
-        // dZ[rows,H] = dl[rows,V] . Wb[H,V]^T ;  dW[H,V] (+)= zb[rows,H]^T . dl[rows,V]
+        zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, d.H + 8);
+        // dZ[rows,H] (bf16) = dl[rows,V] . Wb[H,V]^T ;  dWx[H+8,V] (+)= zb[rows,H+8]^T . dl[rows,V]  (row H = db)
         st = bwd_gemms(d, g, sc, m, nb, rows, xlen, ylen, dW, /*accumulate=*/b0 > 0, s, launches);
         if (st) return st;
-        const int rthreads = ((d.H / 4 + 31) / 32) * 32;
+        const int rthreads = ((d.H / 8 + 31) / 32) * 32;
         ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", s);
         denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
         delete t1; t1 = new ScopedTimer("dpred_rows_kernel", s);
         dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_pred);
-        delete t1; t1 = new ScopedTimer("db_kernel", s);
-        db_kernel<<<dim3(d.V / 64, 64), 256, 0, s>>>(sc.dl, xlen, ylen, m, nb, d.V, db);
         delete t1;
         *launches += 4;
         if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
     }
+    if (cudaMemcpyAsync(dW, sc.dWx, sizeof(float) * (size_t)d.H * d.V, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(db, sc.dWx + (size_t)d.H * d.V, sizeof(float) * d.V, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+        return RNNT_STATUS_MEMOPS_FAILED;
     return RNNT_STATUS_SUCCESS;
 }
 

@@ -173,8 +173,9 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                     uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
                     for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
                     if (p.zb) {
-                        uint4* z4p = reinterpret_cast<uint4*>(p.zb + (size_t)tile * 128 * p.H);
-                        for (int i = ptid; i < 128 * p.H / 8; i += 256) z4p[i] = z4;
+                        const int h8 = p.H / 8;
+                        for (int i = ptid; i < 128 * h8; i += 256)
+                            *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + i / h8) * p.zld + (i % h8) * 8) = z4;
                     }
                 }
                 continue;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                     *reinterpret_cast<uint4*>(stg + soff[pass]) = packed;
                     if (MODE == 1 && p.zb) {
                         const int r = pass * 32 + pw * 4 + (lane >> 3);
-                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.H + kb * 64 + (lane & 7) * 8) = packed;
+                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.zld + kb * 64 + (lane & 7) * 8) = packed;
                     }
                 }
                 ptx::named_bar_sync(1, 256);

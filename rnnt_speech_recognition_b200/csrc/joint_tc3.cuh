@@ -185,8 +185,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                     uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
                     for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
                     if (p.zb) {
-                        uint4* z4p = reinterpret_cast<uint4*>(p.zb + (size_t)tile * 128 * p.H);
-                        for (int i = ptid; i < 128 * p.H / 8; i += 256) z4p[i] = z4;
+                        const int h8 = p.H / 8;
+                        for (int i = ptid; i < 128 * h8; i += 256)
+                            *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + i / h8) * p.zld + (i % h8) * 8) = z4;
                     }
                 }
                 continue;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
                 if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
                 if (MODE == 1 && p.zb) {
-                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r2) * p.H + kb * 64 + hh * 32);
+                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r2) * p.zld + kb * 64 + hh * 32);
                     zdst[0] = make_uint4(zr[0], zr[1], zr[2], zr[3]);   zdst[1] = make_uint4(zr[4], zr[5], zr[6], zr[7]);
                     zdst[2] = make_uint4(zr[8], zr[9], zr[10], zr[11]); zdst[3] = make_uint4(zr[12], zr[13], zr[14], zr[15]);
                 }

@@ -45,3 +45,25 @@ def test_bf16_vs_fp32_at_c2():
         assert_close(a, b, rtol=0, atol=0, ntol=BF16_GRAD_NTOL, what=n)
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
         assert rel < 1e-2, (n, rel)
+
+
+def test_bf16_common_voice_shaped_batch():
+    """BASELINE C5 in miniature: ragged T_b, U_b (one long and one minimal utterance), V=4096, H=640,
+    maxU=200 (8-wide u-tiles) -- bf16 tensor-core path against the fp32 exact path."""
+    rng = np.random.default_rng(11)
+    B, T, U, V, H = 4, 160, 200, 4096, 640
+    k = synth(B, T, U, V, H, 11, ragged=False)
+    k["input_lengths"] = np.array([T, 10, 97, 160], np.int32)
+    k["label_lengths"] = np.array([U - 1, 9, 120, 30], np.int32)
+    for b in range(B):
+        k["labels"][b, k["label_lengths"][b]:] = 0
+    c32, g32 = run_joint(k, "fp32")
+    c16, g16 = run_joint(k, "bf16")
+    assert np.all(np.isfinite(c16))
+    assert_close(c16, c32, rtol=BF16_COST_RTOL, atol=1e-2, what="costs")
+    for a, b_, n in zip(g16, g32, ("d_enc", "d_pred", "dW", "db")):
+        assert np.all(np.isfinite(a)), n
+        rel = np.linalg.norm(a - b_) / np.linalg.norm(b_)
+        assert rel < 1e-2, (n, rel)
+    for b in range(B):   # padded positions exactly zero
+        assert not g16[0][b, k["input_lengths"][b]:].any() and not g16[1][b, k["label_lengths"][b] + 1:].any()
