@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                 const int lab = (rv && u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
                 const long long cell = ((long long)ti.b * p.maxT + t) * p.maxU + u;
                 float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f;  // MODE 0 state (log2 domain)
-                float kd2 = -CUDART_INF_F, cg = 0.f, csb = 0.f, csl = 0.f;  // MODE 1 coefficients
+                float kd2 = -CUDART_INF_F, cg = 0.f, csb = 0.f, csl = 0.f;  // MODE 1: exponent offset, scale, final dl[blank], final dl[label]
                 if (MODE == 1 && rv) {
                     const float4 cf = p.coef[cell];
                     kd2 = cf.x * LOG2E; cg = cf.y; csb = cf.z; csl = cf.w;
@@ -309,18 +309,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
 #pragma unroll
                             for (int i = 0; i < 32; ++i) yl = (i == d) ? y[i] : yl;
                         } else {
-                            const int d = lab - col0, db = p.blank - col0;
                             uint32_t o[16];
 #pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                float d0 = cg * ptx::ex2_approx(y[i] + kd2);
-                                float d1 = cg * ptx::ex2_approx(y[i + 1] + kd2);
-                                if (i == db) d0 -= csb;
-                                if (i + 1 == db) d1 -= csb;
-                                if (i == d) d0 -= csl;
-                                if (i + 1 == d) d1 -= csl;
-                                o[i >> 1] = ptx::pack_bf16x2(d0, d1);
-                            }
+                            for (int i = 0; i < 32; i += 2)
+                                o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
                             uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
                             dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                             dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -331,6 +323,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+                }
+                if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
+                    __nv_bfloat16* drow = p.dl + ((size_t)tile * 128 + r) * p.V;
+                    drow[p.blank] = __float2bfloat16(csb);
+                    if (lab >= 0) drow[lab] = __float2bfloat16(csl);
                 }
                 if (MODE == 0 && rv) {
                     const float lse2 = m2 + log2f(s);
@@ -407,8 +404,13 @@ __device__ __forceinline__ void store_f32x8(float* p, const F8& a) {
     *reinterpret_cast<float4*>(p) = make_float4(a.v[0], a.v[1], a.v[2], a.v[3]);
     *reinterpret_cast<float4*>(p + 4) = make_float4(a.v[4], a.v[5], a.v[6], a.v[7]);
 }
-// grid (maxT, nb): d_enc[b,t,:] = sum_u g
-__global__ void __launch_bounds__(128) denc_rows_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ enc,
+// Pass 1, grid (maxT, nb): g = dZ * sech^2(enc+pred) is computed ONCE, written back in place (bf16) and summed over u:
+//   d_enc[b,t,:] = sum_u g
+__device__ __forceinline__ void store_bf16x8(__nv_bfloat16* p, const F8& a) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(ptx::pack_bf16x2(a.v[0], a.v[1]), ptx::pack_bf16x2(a.v[2], a.v[3]),
+                                              ptx::pack_bf16x2(a.v[4], a.v[5]), ptx::pack_bf16x2(a.v[6], a.v[7]));
+}
+__global__ void __launch_bounds__(128) denc_rows_kernel(__nv_bfloat16* __restrict__ dz, const float* __restrict__ enc,
                                                         const float* __restrict__ pred, const int* __restrict__ xlen,
                                                         const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
                                                         int H, float* __restrict__ d_enc) {
@@ -422,19 +424,21 @@ __global__ void __launch_bounds__(128) denc_rows_kernel(const __nv_bfloat16* __r
         const F8 e = load_f32x8(enc + ((size_t)b * maxT + t) * H + h);
 #pragma unroll 4
         for (int u = 0; u < Un; ++u) {
-            const F8 d = load_bf16x8(dz + tile_row(m, b, t, u) * H + h);
+            __nv_bfloat16* row = dz + tile_row(m, b, t, u) * H + h;
+            const F8 d = load_bf16x8(row);
             const F8 q = load_f32x8(pred + ((size_t)b * maxU + u) * H + h);
+            F8 g;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc.v[i] += d.v[i] * sech2(e.v[i] + q.v[i]);
+            for (int i = 0; i < 8; ++i) { g.v[i] = d.v[i] * sech2(e.v[i] + q.v[i]); acc.v[i] += g.v[i]; }
+            store_bf16x8(row, g);
         }
     }
     store_f32x8(d_enc + ((size_t)b * maxT + t) * H + h, acc);
 }
-// grid (maxU, nb): d_pred[b,u,:] = sum_t g
-__global__ void __launch_bounds__(128) dpred_rows_kernel(const __nv_bfloat16* __restrict__ dz, const float* __restrict__ enc,
-                                                         const float* __restrict__ pred, const int* __restrict__ xlen,
-                                                         const int* __restrict__ ylen, RowMap m, int maxT, int maxU,
-                                                         int H, float* __restrict__ d_pred) {
+// Pass 2, grid (maxU, nb): d_pred[b,u,:] = sum_t g   (pure sum over the rows pass 1 rewrote)
+__global__ void __launch_bounds__(128) dpred_rows_kernel(const __nv_bfloat16* __restrict__ g, const int* __restrict__ xlen,
+                                                         const int* __restrict__ ylen, RowMap m, int maxU, int H,
+                                                         float* __restrict__ d_pred) {
     const int u = blockIdx.x, b = m.b0 + blockIdx.y, h = threadIdx.x * 8;
     if (h >= H) return;
     const int Tn = xlen[b], Un = ylen[b] + 1;
@@ -442,13 +446,11 @@ __global__ void __launch_bounds__(128) dpred_rows_kernel(const __nv_bfloat16* __
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
     if (u < Un) {
-        const F8 q = load_f32x8(pred + ((size_t)b * maxU + u) * H + h);
-#pragma unroll 4
+#pragma unroll 8
         for (int t = 0; t < Tn; ++t) {
-            const F8 d = load_bf16x8(dz + tile_row(m, b, t, u) * H + h);
-            const F8 e = load_f32x8(enc + ((size_t)b * maxT + t) * H + h);
+            const F8 d = load_bf16x8(g + tile_row(m, b, t, u) * H + h);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc.v[i] += d.v[i] * sech2(e.v[i] + q.v[i]);
+            for (int i = 0; i < 8; ++i) acc.v[i] += d.v[i];
         }
     }
     store_f32x8(d_pred + ((size_t)b * maxU + u) * H + h, acc);
@@ -704,7 +706,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", s);
         denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
         delete t1; t1 = new ScopedTimer("dpred_rows_kernel", s);
-        dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_pred);
+        dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, s>>>(sc.dz, xlen, ylen, m, d.maxU, d.H, d_pred);
         delete t1;
         *launches += 4;
         if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;

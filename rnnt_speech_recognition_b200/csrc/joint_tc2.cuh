@@ -317,18 +317,10 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
 #pragma unroll
                         for (int i = 0; i < 32; ++i) yl = (i == d) ? y[i] : yl;
                     } else {
-                        const int d = lab - col0, db = p.blank - col0;
                         uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float d0 = cg * ptx::ex2_approx(y[i] + kd2);
-                            float d1 = cg * ptx::ex2_approx(y[i + 1] + kd2);
-                            if (i == db) d0 -= csb;
-                            if (i + 1 == db) d1 -= csb;
-                            if (i == d) d0 -= csl;
-                            if (i + 1 == d) d1 -= csl;
-                            o[i >> 1] = ptx::pack_bf16x2(d0, d1);
-                        }
+                        for (int i = 0; i < 32; i += 2)
+                            o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
                         uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
                         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -339,6 +331,11 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+            }
+            if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
+                __nv_bfloat16* drow = p.dl + ((size_t)tile * 128 + r) * p.V;
+                drow[p.blank] = __float2bfloat16(csb);
+                if (lab >= 0) drow[lab] = __float2bfloat16(csl);
             }
             if (MODE == 0 && rv) {
                 const float lse2 = m2 + log2f(s);

@@ -23,10 +23,11 @@ inline Tc2Geom tc3_geometry(int H, int V) {
     if (!g.ok) return g;
     // smem: enc/pred ring (2 x (2 x 16 KB pred boxes + 4 KB enc box)) + W ring; W stages shrink to fit
     const size_t in_bytes = (size_t)TC3_IN_STAGES * (2 * 16384 + 4096);
-    const size_t budget = 232448 - 1024 - 1024 - in_bytes;
+    const size_t bias_bytes = V <= 4096 ? (size_t)V * 4 : 0;
+    const size_t budget = 232448 - 1024 - 1024 - in_bytes - 16384 /*epilogue label-pick scratch*/ - bias_bytes;
     g.stages = (int)(budget / ((size_t)g.ks * 8192));
     if (g.stages > 6) g.stages = 6;
-    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024;
+    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024 + 16384 + bias_bytes;
     g.ok = g.stages >= 2;
     return g;
 }
@@ -54,6 +55,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     uint64_t* in_full = acc_empty + TC2_MAX_NBUF;         // [TC3_IN_STAGES]  input TMA -> producers
     uint64_t* in_empty = in_full + TC3_IN_STAGES;         // [TC3_IN_STAGES]  producers -> input TMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + TC3_IN_STAGES);
+    uint8_t* ysm = reinterpret_cast<uint8_t*>(bars) + 1024;   // 128 threads x 32 floats: label-logit pick (MODE 0)
+    float* bias2 = reinterpret_cast<float*>(ysm + 16384);      // bias * log2(e) for V <= 4096 (else read from global)
+    const bool bias_in_smem = p.V <= 4096;
+    if (bias_in_smem)
+        for (int i = threadIdx.x; i < p.V; i += TC3_THREADS) bias2[i] = __ldg(p.bias + i) * 1.4426950408889634f;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
@@ -258,7 +264,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                     ptx::tmem_ld_wait();
                     if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
                     const int col0 = c * NC + j * 32;
-                    const float bv = __ldg(p.bias + col0 + lane) * LOG2E;
+                    const float bv = bias_in_smem ? bias2[col0 + lane] : __ldg(p.bias + col0 + lane) * LOG2E;
                     float y[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -278,22 +284,25 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                             for (int i = 0; i < 32; ++i)
                                 if (col0 + i == p.blank) yb = y[i];
                         }
+                        // logit[label_u]: the label differs per thread, so the wanted element sits at a DYNAMIC index of
+                        // this thread's 32 registers.  Instead of 32 compare+select pairs, the group is parked in a
+                        // thread-private, XOR-swizzled (conflict-free) smem row and one element is read back -- only
+                        // when some lane of the warp has its label in this column group.
                         const int d = lab - col0;
+                        const bool mine = (unsigned)d < 32u;
+                        if (__any_sync(0xffffffffu, mine)) {
+                            uint8_t* yrow = ysm + (size_t)(warp * 32 + lane) * 128;
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) yl = (i == d) ? y[i] : yl;
+                            for (int cc = 0; cc < 8; ++cc)
+                                *reinterpret_cast<float4*>(yrow + ((cc ^ (lane & 7)) << 4)) =
+                                    make_float4(y[4 * cc], y[4 * cc + 1], y[4 * cc + 2], y[4 * cc + 3]);
+                            if (mine) yl = *reinterpret_cast<const float*>(yrow + ((((d >> 2) ^ (lane & 7)) << 4) + ((d & 3) << 2)));
+                        }
                     } else {
-                        const int d = lab - col0, db = p.blank - col0;
                         uint32_t o[16];
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) {
-                            float d0 = cg * ptx::ex2_approx(y[i] + kd2);
-                            float d1 = cg * ptx::ex2_approx(y[i + 1] + kd2);
-                            if (i == db) d0 -= csb;
-                            if (i + 1 == db) d1 -= csb;
-                            if (i == d) d0 -= csl;
-                            if (i + 1 == d) d1 -= csl;
-                            o[i >> 1] = ptx::pack_bf16x2(d0, d1);
-                        }
+                        for (int i = 0; i < 32; i += 2)
+                            o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
                         uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
                         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
@@ -304,6 +313,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+            }
+            if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
+                __nv_bfloat16* drow = p.dl + ((size_t)tile * 128 + r) * p.V;
+                drow[p.blank] = __float2bfloat16(csb);
+                if (lab >= 0) drow[lab] = __float2bfloat16(csl);
             }
             if (MODE == 0 && rv) {
                 const float lse2 = m2 + log2f(s);

@@ -245,13 +245,17 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(const T* logits, T* out,
 
 // ---------------------------------------------------------------------------------------------
 // Per-cell coefficients for the fused (tensor-core) backward epilogue, natural cell order:
-//   coef[cell] = (kd, g, g*sb, g*sl) with dlogit[v] = g*exp(x_v + kd) - [v==blank] g*sb - [v==label] g*sl
+//   coef[cell] = (kd, g, dl_blank, dl_label): dlogit[v] = g*exp(x_v + kd) for every v EXCEPT the two special columns,
+//   whose final values are precomputed here from the forward's cached log-probs (x_v + kd == lp_v + alpha + beta - ll):
+//     dl_blank = g*(exp(lpb + a + b - ll) - sb),  dl_label = g*(exp(lpl + a + b - ll) - sl)
+//   with sb / sl the outgoing-arc terms of gpu_rnnt_kernel.h:163-172.  The epilogue then needs no per-element
+//   compare/subtract: it overwrites those two entries after the bulk store.
 // Invalid (padded) cells get (-inf, 0, 0, 0) so that their rows contribute exactly 0.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) cell_coef_kernel(long long ncells, const int* __restrict__ xlen,
-                                                        const int* __restrict__ ylen, int maxT, int maxU,
-                                                        long long SK, const float* __restrict__ lse,
-                                                        const float* __restrict__ lpb,
+                                                        const int* __restrict__ ylen, const int* __restrict__ labels,
+                                                        int blank, int maxT, int maxU, long long SK,
+                                                        const float* __restrict__ lse, const float* __restrict__ lpb,
                                                         const float* __restrict__ lpl,
                                                         const float* __restrict__ alphas,
                                                         const float* __restrict__ betas,
@@ -265,11 +269,15 @@ __global__ void __launch_bounds__(256) cell_coef_kernel(long long ncells, const 
     if (c.t < Tn && c.u < Un) {
         const long long k = sk_index(c.b, c.t, c.u, maxU, SK);
         const float a = alphas[k], bt = betas[k], ll = llf[c.b], g = gscale ? gscale[c.b] : 1.f;
-        float sb = 0.f, sl = 0.f;
+        const float occ = a + bt - ll;                                   // log occupancy of the cell
+        float sb = 0.f, sl = 0.f, pl = 0.f;
         if (c.t == Tn - 1 && c.u == Un - 1) sb = expf(a + lpb[k] - ll);
         if (c.t < Tn - 1) sb = expf(a + lpb[k] - ll + betas[k + maxU]);
-        if (c.u < Un - 1) sl = expf(a + lpl[k] - ll + betas[k + maxU + 1]);
-        o = make_float4(a + bt - ll - lse[cell], g, g * sb, g * sl);
+        const bool has_label = c.u < Un - 1;
+        if (has_label) { sl = expf(a + lpl[k] - ll + betas[k + maxU + 1]); pl = expf(lpl[k] + occ); }
+        float dlb = g * (expf(lpb[k] + occ) - sb), dll = g * (pl - sl);
+        if (has_label && labels[(long long)c.b * (maxU - 1) + c.u] == blank) { dlb -= g * sl; dll = dlb; }  // degenerate: label == blank
+        o = make_float4(occ - lse[cell], g, dlb, dll);
     }
     coef[cell] = o;
 }

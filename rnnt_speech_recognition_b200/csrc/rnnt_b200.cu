@@ -358,7 +358,7 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
     const long long N = (long long)d.B * d.maxT * d.maxU;
     rb::ScopedTimer* tmc = new rb::ScopedTimer("cell_coef_kernel", s);
     rb::cell_coef_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(
-        N, input_lengths, label_lengths, d.maxT, d.maxU, skew_plane(d.maxT, d.maxU), ws.loss.lse, ws.loss.lpb,
+        N, input_lengths, label_lengths, labels, d.blank_label, d.maxT, d.maxU, skew_plane(d.maxT, d.maxU), ws.loss.lse, ws.loss.lpb,
         ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf, grad_costs, ws.coef);
     delete tmc;
     RB_LAUNCHED(1);
