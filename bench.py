@@ -41,6 +41,19 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def measured_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/rNN/traffic.json), or None."""
+    import glob
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")), reverse=True):
+        try:
+            t = json.load(open(f)).get(kernel)
+            if t:
+                return t["dram_bytes_per_launch"]
+        except Exception:
+            pass
+    return None
+
+
 def synth(cfg, seed, device, pin=False):
     import torch
     g = torch.Generator().manual_seed(seed)
@@ -285,7 +298,7 @@ def main():
             ach = flops / (t_dom * 1e-3) / 1e12 if t_dom else None
             peak = pk["bf16_tflops_sustained"]
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": None,
+                    "frac": (ach / peak) if ach else None, "traffic": measured_traffic(dom),
                     "peak_source": "%s bf16 sustained (kernel timed inside the step)" % pk_src,
                     "algorithmic_flops_per_launch": flops, "launch_ms": t_dom,
                     "step": {"algorithmic_flops": 6.0 * N * H * V,
@@ -297,7 +310,7 @@ def main():
             byts = 24.0 * N
             ach = byts / (t_dom * 1e-3) / 1e9 if t_dom else None
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": (ach / pk["hbm_gbs"]) if ach else None, "traffic": None, "peak_source": pk_src,
+                    "frac": (ach / pk["hbm_gbs"]) if ach else None, "traffic": measured_traffic(dom), "peak_source": pk_src,
                     "algorithmic_bytes_per_launch": byts, "launch_ms": t_dom}
         h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "pred", "labels", "il", "ll"))
         out = {

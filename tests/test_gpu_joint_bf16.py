@@ -67,3 +67,22 @@ def test_bf16_common_voice_shaped_batch():
         assert rel < 1e-2, (n, rel)
     for b in range(B):   # padded positions exactly zero
         assert not g16[0][b, k["input_lengths"][b]:].any() and not g16[1][b, k["label_lengths"][b] + 1:].any()
+
+
+@pytest.mark.parametrize("B,T,U,V,H,blank", [(3, 9, 1, 64, 64, 0),      # empty transcripts (U == 1)
+                                             (3, 1, 5, 64, 128, 0),     # a single encoder frame
+                                             (2, 12, 6, 128, 64, 5)])   # blank index != 0
+def test_bf16_edge_lattices(oracle, B, T, U, V, H, blank):
+    rng = np.random.default_rng(21)
+    k = synth(B, T, max(U, 2), V, H, 21, ragged=False)
+    k["pred"] = k["pred"][:, :U].copy()
+    cand = np.array([v for v in range(V) if v != blank])
+    k["labels"] = rng.choice(cand, size=(B, U - 1)).astype(np.int32) if U > 1 else np.zeros((B, 0), np.int32)
+    k["label_lengths"] = np.full(B, U - 1, np.int32)
+    k["blank"] = np.int32(blank)
+    o = oracle.joint_loss_grad(*(k[n].astype(np.float64) for n in ("enc", "pred", "W", "b")), k["labels"],
+                               k["input_lengths"], k["label_lengths"], blank, grad_scale=np.full(B, 1.0 / B))
+    costs, grads = run_joint(k, "bf16")
+    assert_close(costs, o["costs"], rtol=BF16_COST_RTOL, atol=1e-2, what="costs")
+    for g, n in zip(grads, ("d_enc", "d_pred", "dW", "db")):
+        assert_close(g, o[n], rtol=0, atol=0, ntol=BF16_GRAD_NTOL, what=n)
