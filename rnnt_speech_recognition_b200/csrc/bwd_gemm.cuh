@@ -15,28 +15,33 @@ inline cublasHandle_t tc_cublas() {
     return h;
 }
 
-inline rnntStatus_t bwd_gemms(const rnntb200JointDesc& d, const TcGeom& g, const TcScratch& sc, const RowMap& m,
-                              int nb, size_t rows, const int* xlen, const int* ylen, float* dW, bool accumulate,
-                              cudaStream_t s, unsigned* launches) {
-    (void)g; (void)m; (void)nb; (void)xlen; (void)ylen;
+inline rnntStatus_t bwd_gemm_dz(const rnntb200JointDesc& d, const TcScratch& sc, size_t rows, cudaStream_t s,
+                                unsigned* launches) {
     cublasHandle_t h = tc_cublas();
     if (!h || cublasSetStream(h, s) != CUBLAS_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
-    const float one = 1.f, zero = 0.f, beta = accumulate ? 1.f : 0.f;
-    ScopedTimer* t = new ScopedTimer("gemm dZ=dl.W^T (cublas)", s);
+    const float one = 1.f, zero = 0.f;
+    ScopedTimer t("gemm dZ=dl.W^T (cublas)", s);
     // row-major dZ[rows,H] == column-major [H,rows] = Wb_cm[V,H]^T . dl_cm[V,rows]
     if (cublasGemmEx(h, CUBLAS_OP_T, CUBLAS_OP_N, d.H, (int)rows, d.V, &one, sc.Wb, CUDA_R_16BF, d.V, sc.dl,
                      CUDA_R_16BF, d.V, &zero, sc.dz, CUDA_R_16BF, d.H, CUBLAS_COMPUTE_32F,
                      CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
         return RNNT_STATUS_EXECUTION_FAILED;
-    delete t; t = new ScopedTimer("gemm dW=z^T.dl (cublas)", s);
+    *launches += 1;
+    return RNNT_STATUS_SUCCESS;
+}
+
+inline rnntStatus_t bwd_gemm_dw(const rnntb200JointDesc& d, const TcScratch& sc, size_t rows, bool accumulate,
+                                cudaStream_t s, unsigned* launches) {
+    cublasHandle_t h = tc_cublas();
+    if (!h || cublasSetStream(h, s) != CUBLAS_STATUS_SUCCESS) return RNNT_STATUS_EXECUTION_FAILED;
+    const float one = 1.f, beta = accumulate ? 1.f : 0.f;
+    ScopedTimer t("gemm dW=z^T.dl (cublas)", s);
     // row-major dWx[H+8,V] == column-major [V,H+8] = dl_cm[V,rows] . zb_cm[H+8,rows]^T
-    (void)dW;
     if (cublasGemmEx(h, CUBLAS_OP_N, CUBLAS_OP_T, d.V, d.H + 8, (int)rows, &one, sc.dl, CUDA_R_16BF, d.V, sc.zb,
                      CUDA_R_16BF, d.H + 8, &beta, sc.dWx, CUDA_R_32F, d.V, CUBLAS_COMPUTE_32F,
                      CUBLAS_GEMM_DEFAULT) != CUBLAS_STATUS_SUCCESS)
         return RNNT_STATUS_EXECUTION_FAILED;
-    delete t;
-    *launches += 2;
+    *launches += 1;
     return RNNT_STATUS_SUCCESS;
 }
 

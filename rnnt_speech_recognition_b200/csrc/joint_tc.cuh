@@ -681,6 +681,22 @@ inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, con
 
 namespace rb {
 
+// Library-owned side stream for the fork/join inside the backward (created once per process).
+struct SideStream {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+    bool ok = false;
+};
+inline SideStream& side_stream() {
+    static SideStream ss;
+    if (!ss.ok) {
+        ss.ok = cudaStreamCreateWithFlags(&ss.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) == cudaSuccess;
+    }
+    return ss;
+}
+
 inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                 const float* W, const float* bias, const int* labels, const int* ylen,
                                 const int* xlen, const float* lse, const float4* coef, float* d_enc, float* d_pred,
@@ -699,16 +715,28 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         rnntStatus_t st = tc_dispatch<1>(d, g, sc, p, s);
         if (st) return st;
         zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, d.H + 8);
-        // dZ[rows,H] (bf16) = dl[rows,V] . Wb[H,V]^T ;  dWx[H+8,V] (+)= zb[rows,H+8]^T . dl[rows,V]  (row H = db)
-        st = bwd_gemms(d, g, sc, m, nb, rows, xlen, ylen, dW, /*accumulate=*/b0 > 0, s, launches);
+        // dZ[rows,H] (bf16) = dl[rows,V] . Wb[H,V]^T, then two independent branches:
+        //   side stream : g = dZ*sech^2 -> d_enc, d_pred        (memory / MUFU bound)
+        //   main stream : dWx[H+8,V] (+)= zb^T . dl  (row H = db) (tensor bound)
+        st = bwd_gemm_dz(d, sc, rows, s, launches);
         if (st) return st;
-        const int rthreads = ((d.H / 8 + 31) / 32) * 32;
-        ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", s);
-        denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, s>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
-        delete t1; t1 = new ScopedTimer("dpred_rows_kernel", s);
-        dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, s>>>(sc.dz, xlen, ylen, m, d.maxU, d.H, d_pred);
-        delete t1;
-        *launches += 4;
+        SideStream& ss = side_stream();
+        if (!ss.ok) return RNNT_STATUS_EXECUTION_FAILED;
+        cudaEventRecord(ss.fork, s);
+        cudaStreamWaitEvent(ss.stream, ss.fork, 0);
+        {
+            const int rthreads = ((d.H / 8 + 31) / 32) * 32;
+            ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", ss.stream);
+            denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, ss.stream>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
+            delete t1; t1 = new ScopedTimer("dpred_rows_kernel", ss.stream);
+            dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, ss.stream>>>(sc.dz, xlen, ylen, m, d.maxU, d.H, d_pred);
+            delete t1;
+        }
+        cudaEventRecord(ss.join, ss.stream);
+        st = bwd_gemm_dw(d, sc, rows, /*accumulate=*/b0 > 0, s, launches);
+        if (st) return st;
+        cudaStreamWaitEvent(s, ss.join, 0);
+        *launches += 3;
         if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
     }
     if (cudaMemcpyAsync(dW, sc.dWx, sizeof(float) * (size_t)d.H * d.V, cudaMemcpyDeviceToDevice, s) != cudaSuccess ||
