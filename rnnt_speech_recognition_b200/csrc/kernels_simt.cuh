@@ -118,6 +118,105 @@ __global__ void __launch_bounds__(256) lse_gather_kernel(const T* __restrict__ l
     }
 }
 
+// float4 fast path of lse_gather (V % 4 == 0, 16-byte aligned rows): each lane streams 16-byte pieces of the row;
+// rows of up to 1024 logits are held in registers between the max and the sum pass (ONE read of the logits),
+// longer rows take the second pass from L1/L2.
+template <int MAXV4>   // per-lane float4 capacity held in registers (8 -> V <= 1024); 0 -> always two passes
+__global__ void __launch_bounds__(256) lse_gather_vec_kernel(const float* __restrict__ logits, long long row0,
+                                                             long long nrows, int V, const int* __restrict__ xlen,
+                                                             const int* __restrict__ ylen,
+                                                             const int* __restrict__ labels, int maxT, int maxU,
+                                                             long long SK, int blank, float* __restrict__ lse,
+                                                             float* __restrict__ lpb, float* __restrict__ lpl) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const long long cell = row0 + row;
+    const CellIdx c = decode_cell(cell, maxT, maxU);
+    const int Tn = xlen[c.b], Un = ylen[c.b] + 1;
+    if (c.t >= Tn || c.u >= Un) return;
+    const float* x = logits + row * (long long)V;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const int n4 = V >> 2;
+    float m = -CUDART_INF_F, s = 0.f;
+    if (MAXV4 > 0 && n4 <= MAXV4 * 32) {
+        float4 r[MAXV4 > 0 ? MAXV4 : 1];
+#pragma unroll
+        for (int i = 0; i < MAXV4; ++i) {
+            const int k = lane + 32 * i;
+            r[i] = (k < n4) ? __ldg(x4 + k) : make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            m = fmaxf(m, fmaxf(fmaxf(r[i].x, r[i].y), fmaxf(r[i].z, r[i].w)));
+        }
+        m = warp_max(m);
+#pragma unroll
+        for (int i = 0; i < MAXV4; ++i) s += expf(r[i].x - m) + expf(r[i].y - m) + expf(r[i].z - m) + expf(r[i].w - m);
+    } else {
+        for (int k = lane; k < n4; k += 32) {
+            const float4 v = __ldg(x4 + k);
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+        m = warp_max(m);
+        for (int k = lane; k < n4; k += 32) {
+            const float4 v = __ldg(x4 + k);
+            s += expf(v.x - m) + expf(v.y - m) + expf(v.z - m) + expf(v.w - m);
+        }
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        const float l = m + logf(s);
+        lse[cell] = l;
+        const long long k = sk_index(c.b, c.t, c.u, maxU, SK);
+        lpb[k] = x[blank] - l;
+        if (c.u < Un - 1) lpl[k] = x[labels[(long long)c.b * (maxU - 1) + c.u]] - l;
+    }
+}
+
+// float4 fast path of rnnt_grad_kernel (same arithmetic, 16-byte loads/stores).
+__global__ void __launch_bounds__(256) rnnt_grad_vec_kernel(const float* logits, float* out, long long row0,
+                                                            long long nrows, int V, const int* __restrict__ xlen,
+                                                            const int* __restrict__ ylen,
+                                                            const int* __restrict__ labels, int maxT, int maxU,
+                                                            long long SK, int blank, const float* __restrict__ lse,
+                                                            const float* __restrict__ alphas,
+                                                            const float* __restrict__ betas,
+                                                            const float* __restrict__ llf,
+                                                            const float* __restrict__ gscale) {
+    const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (row >= nrows) return;
+    const long long cell = row0 + row;
+    const CellIdx c = decode_cell(cell, maxT, maxU);
+    const int Tn = xlen[c.b], Un = ylen[c.b] + 1;
+    const float* x = logits + row * (long long)V;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    float4* g4 = reinterpret_cast<float4*>(out + row * (long long)V);
+    const int n4 = V >> 2;
+    if (c.t >= Tn || c.u >= Un) {
+        for (int k = lane; k < n4; k += 32) g4[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    const long long k0 = sk_index(c.b, c.t, c.u, maxU, SK);
+    const float a = alphas[k0], bt = betas[k0], ll = llf[c.b], l = lse[cell];
+    const float gs = gscale ? gscale[c.b] : 1.f;
+    const int label = (c.u < Un - 1) ? labels[(long long)c.b * (maxU - 1) + c.u] : -1;
+    float sb = 0.f, sl = 0.f;
+    if (c.t == Tn - 1 && c.u == Un - 1) sb = expf(a + (x[blank] - l) - ll);
+    if (c.t < Tn - 1) sb = expf(a + (x[blank] - l) - ll + betas[k0 + maxU]);
+    if (label >= 0) sl = expf(a + (x[label] - l) - ll + betas[k0 + maxU + 1]);
+    const float kd = a + bt - ll - l;
+    for (int k = lane; k < n4; k += 32) {
+        const float4 v = x4[k];
+        float4 g = make_float4(expf(v.x + kd), expf(v.y + kd), expf(v.z + kd), expf(v.w + kd));
+        const int db = blank - (k << 2), dl = label - (k << 2);
+        g.x -= (db == 0 ? sb : 0.f) + (dl == 0 ? sl : 0.f);
+        g.y -= (db == 1 ? sb : 0.f) + (dl == 1 ? sl : 0.f);
+        g.z -= (db == 2 ? sb : 0.f) + (dl == 2 ? sl : 0.f);
+        g.w -= (db == 3 ? sb : 0.f) + (dl == 3 ? sl : 0.f);
+        g.x *= gs; g.y *= gs; g.z *= gs; g.w *= gs;
+        g4[k] = g;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // alpha / beta wavefronts.  grid = (B, 2): blockIdx.y == 0 runs alpha, 1 runs beta, so the two
 // recurrences of one utterance overlap on different SMs.  Thread u owns lattice column u and

@@ -77,18 +77,34 @@ rnntStatus_t loss_op(const T* acts, T* grads, const int* labels, const int* ylen
     LossWs<T> w(workspace, B, maxT, maxU);
     const long long N = (long long)B * maxT * maxU, SK = skew_plane(maxT, maxU);
     const unsigned blocks = (unsigned)((N * 32 + 255) / 256);
+    // 16-byte fast paths need float data, V % 4 == 0 and 16-byte aligned tensors (rows then stay aligned)
+    const bool vec = sizeof(T) == 4 && (V % 4) == 0 && ((uintptr_t)acts % 16) == 0 && (!grads || ((uintptr_t)grads % 16) == 0);
     {
         rb::ScopedTimer tm("lse_gather_kernel", s);
-        rb::lse_gather_kernel<T><<<blocks, 256, 0, s>>>(acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK, blank,
-                                                        w.lse, w.lpb, w.lpl);
+        if (vec) {
+            if (V <= 1024)
+                rb::lse_gather_vec_kernel<8><<<blocks, 256, 0, s>>>((const float*)acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
+                                                                    blank, (float*)w.lse, (float*)w.lpb, (float*)w.lpl);
+            else
+                rb::lse_gather_vec_kernel<0><<<blocks, 256, 0, s>>>((const float*)acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
+                                                                    blank, (float*)w.lse, (float*)w.lpb, (float*)w.lpl);
+        } else {
+            rb::lse_gather_kernel<T><<<blocks, 256, 0, s>>>(acts, 0, N, V, xlen, ylen, labels, maxT, maxU, SK, blank,
+                                                            w.lse, w.lpb, w.lpl);
+        }
     }
     RB_LAUNCHED(1);
     if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     if (launch_alpha_beta(w, xlen, ylen, B, maxT, maxU, s)) return RNNT_STATUS_EXECUTION_FAILED;
     if (grads) {
         rb::ScopedTimer tm("rnnt_grad_kernel", s);
-        rb::rnnt_grad_kernel<T><<<blocks, 256, 0, s>>>(acts, grads, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
-                                                       blank, w.lse, w.alphas, w.betas, w.llf, gscale);
+        if (vec)
+            rb::rnnt_grad_vec_kernel<<<blocks, 256, 0, s>>>((const float*)acts, (float*)grads, 0, N, V, xlen, ylen, labels, maxT,
+                                                            maxU, SK, blank, (const float*)w.lse, (const float*)w.alphas,
+                                                            (const float*)w.betas, (const float*)w.llf, (const float*)gscale);
+        else
+            rb::rnnt_grad_kernel<T><<<blocks, 256, 0, s>>>(acts, grads, 0, N, V, xlen, ylen, labels, maxT, maxU, SK,
+                                                           blank, w.lse, w.alphas, w.betas, w.llf, gscale);
         RB_LAUNCHED(1);
         if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     }
