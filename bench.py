@@ -30,6 +30,9 @@ WORKLOADS = {
     "c3": dict(B=32, T=512, U=128, V=1024, H=640, precision="bf16", dtype="bf16"),
     "c2": dict(B=16, T=256, U=64, V=256, H=320, precision="fp32", dtype="f32"),
     "c1": dict(B=2, T=20, U=8, V=32, H=64, precision="fp32", dtype="f32"),
+    # BASELINE C5: Common-Voice-shaped ragged batch (seed 1234, T_b ~ U{100..1600}, U_b ~ U{10..200},
+    # one utterance forced to (1600,200) and one to (100,10)); padded/masked lattice stress
+    "c5": dict(B=64, T=1600, U=200, V=4096, H=640, precision="bf16", dtype="bf16", ragged=True),
 }
 METRIC = "rnnt_loss_grad_utterances_per_sec"
 
@@ -62,6 +65,15 @@ def synth(cfg, seed, device, pin=False):
              W=torch.randn(H, V, generator=g) / H ** 0.5, b=torch.zeros(V),
              labels=torch.randint(1, V, (B, U - 1), generator=g, dtype=torch.int32),
              il=torch.full((B,), T, dtype=torch.int32), ll=torch.full((B,), U - 1, dtype=torch.int32))
+    if cfg.get("ragged"):
+        d["il"] = torch.randint(100, T + 1, (B,), generator=g, dtype=torch.int32)
+        d["ll"] = torch.randint(10, U + 1, (B,), generator=g, dtype=torch.int32) - 1
+        d["il"][0], d["ll"][0] = T, U - 1
+        d["il"][1], d["ll"][1] = 100, 9
+        for i in range(B):
+            d["enc"][i, d["il"][i]:] = 0
+            d["pred"][i, d["ll"][i] + 1:] = 0
+            d["labels"][i, d["ll"][i]:] = 0
     if pin:
         return {k: v.pin_memory() for k, v in d.items()}
     return {k: v.to(device) for k, v in d.items()}
@@ -185,8 +197,9 @@ def reference_arm(args, cfg, rank):
 
 
 def workload_config(cfg, n_gpus, name):
-    return {"workload": "BASELINE %s: B=%d T=%d U=%d V=%d H=%d per GPU, joint fwd + alpha/beta + grads (d_enc,d_pred,dW,db)"
-                        % (name.upper(), cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["H"]),
+    return {"workload": "BASELINE %s: B=%d T=%d U=%d V=%d H=%d per GPU%s, joint fwd + alpha/beta + grads (d_enc,d_pred,dW,db)"
+                        % (name.upper(), cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["H"],
+                           " (ragged T_b in [100,T], U_b in [10,U])" if cfg.get("ragged") else ""),
             "global_batch": cfg["B"] * n_gpus, "parallelism": "dp%d" % n_gpus, "precision": cfg["precision"],
             "l2": "256 MiB scratch write between timed steps; per-step working set (>4 GB) exceeds the 126 MB L2"}
 
@@ -309,7 +322,7 @@ def main():
 
     if rank == 0:
         pk, pk_src = peaks()
-        N = B * T * U
+        N = int((d["il"].long() * (d["ll"].long() + 1)).sum().item())      # valid lattice cells (== B*T*U when not ragged)
         if cfg["precision"] == "bf16":
             flops = 2.0 * N * H * V
             dom = next((k for k in kernels if k.endswith("<fwd>")), "joint_tc3_kernel<fwd>")

@@ -132,6 +132,10 @@ typedef struct {
     int blank_label;
     int precision; /* rnntb200Precision */
     CUstream stream;
+    /** 0 (default): the library never synchronises with the host (graph-capturable).  1: the bf16 backward may read
+     *  ONE int (the number of lattice tiles that intersect the valid region) back per utterance chunk, so that
+     *  ragged batches run their GEMMs over the valid rows only instead of the padded lattice. */
+    int allow_host_sync;
 } rnntb200JointDesc;
 
 /** Bytes of device workspace the forward/backward pair needs (pure function of the descriptor). */

@@ -81,6 +81,7 @@ struct JointTcParams {
     int TT, UU, nTb, nUb, NC, NCH, KB, stages;
     long long SK;
     int b0, nb;                 // utterance range of this launch
+    const int* slot;            // optional tile -> compact row-block map of this launch (valid tiles only); NULL = tile order
     int zld;                    // row stride (elements) of zb: H + 8 (the extra 8 columns carry the ones column for db)
     int nbuf, swap, ks, dbg;    // v2 kernel: TMEM accumulator buffers; bf16-pair order of TMEM A; K-blocks per W stage; bring-up switches
     float* lse; float* lpb; float* lpl;              // MODE 0 outputs
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
             if (!ti.valid) {
-                if (MODE == 1) {  // the plain GEMMs reduce over ALL rows: padding tiles must read as zero
+                if (MODE == 1 && !p.slot) {  // uncompacted rows: the plain GEMMs reduce over ALL rows, padding tiles must read as zero
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
                     uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
                     for (int i = threadIdx.x; i < 128 * p.V / 8; i += 256) d4[i] = z4;
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                 }
                 continue;
             }
+            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
             // ---- A operand: z = tanh(enc + pred) -> bf16, SW128 K-major, one 16-byte chunk per thread-task
             // Per-thread task geometry is fixed for the tile: 4 row-passes x one 16-byte chunk column.
             uint32_t eo[4], qo[4], soff[4];   // float4-unit offsets into enc / pred, byte offset into a K block
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                     *reinterpret_cast<uint4*>(zs + (size_t)kb * 16384 + soff[pass]) = packed;
                     if (MODE == 1 && p.zb) {
                         const int r = pass * 32 + warp * 4 + (lane >> 3);
-                        *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r) * p.zld + kb * 64 + (lane & 7) * 8) = packed;
+                        *reinterpret_cast<uint4*>(p.zb + (rowbase + r) * p.zld + kb * 64 + (lane & 7) * 8) = packed;
                     }
                 }
                 ptx::fence_proxy_async_smem();
@@ -313,7 +315,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
 #pragma unroll
                             for (int i = 0; i < 32; i += 2)
                                 o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
-                            uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
+                            uint4* dst = reinterpret_cast<uint4*>(p.dl + (rowbase + r) * p.V + col0);
                             dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                             dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
                             dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
@@ -325,7 +327,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                     if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
                 }
                 if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
-                    __nv_bfloat16* drow = p.dl + ((size_t)tile * 128 + r) * p.V;
+                    __nv_bfloat16* drow = p.dl + (rowbase + r) * p.V;
                     drow[p.blank] = __float2bfloat16(csb);
                     if (lab >= 0) drow[lab] = __float2bfloat16(csl);
                 }
@@ -376,11 +378,49 @@ __device__ __forceinline__ float sech2(float x) {
     const float r = __frcp_rn(1.f + e);                                   // 1+e in [1,2]: one Newton-free reciprocal
     return 4.f * e * r * r;
 }
-struct RowMap { int TT, UU, nTb, nUb, b0, lgUU; };   // TT*UU == 128, both powers of two
+struct RowMap { int TT, UU, nTb, nUb, b0, lgUU; const int* slot; };   // TT*UU == 128, both powers of two
 __device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u) {
     const int lgTT = 7 - m.lgUU;
-    const size_t q = ((size_t)(b - m.b0) * m.nTb + (t >> lgTT)) * m.nUb + (u >> m.lgUU);
+    size_t q = ((size_t)(b - m.b0) * m.nTb + (t >> lgTT)) * m.nUb + (u >> m.lgUU);
+    if (m.slot) q = (size_t)m.slot[q];     // compacted: only valid tiles own rows (callers only ask for valid cells)
     return q * 128 + ((t & (m.TT - 1)) << m.lgUU) + (u & (m.UU - 1));
+}
+// slot[tile] = rank of the tile among the VALID tiles of this launch (-1 if it lies in the padding); *count = #valid.
+// One block; a serial-over-chunks block scan is plenty for the <= ~1e5 tiles of a launch.
+__global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restrict__ xlen, const int* __restrict__ ylen,
+                                                            int b0, int ntiles, int nTb, int nUb, int TT, int UU,
+                                                            int* __restrict__ slot, int* __restrict__ count) {
+    __shared__ int warp_sums[32];
+    __shared__ int base;
+    if (threadIdx.x == 0) base = 0;
+    __syncthreads();
+    const int per_utt = nTb * nUb, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int t0 = 0; t0 < ntiles; t0 += 1024) {
+        const int tile = t0 + threadIdx.x;
+        int v = 0;
+        if (tile < ntiles) {
+            const int bl = tile / per_utt, rem = tile - bl * per_utt, b = b0 + bl;
+            v = ((rem / nUb) * TT < xlen[b] && (rem % nUb) * UU < ylen[b] + 1) ? 1 : 0;
+        }
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += n; }
+        if (lane == 31) warp_sums[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int w = warp_sums[lane], wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int n = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += n; }
+            warp_sums[lane] = wi - w;   // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const int excl = base + warp_sums[warp] + incl - v;
+        if (tile < ntiles) slot[tile] = v ? excl : -1;
+        __syncthreads();
+        if (threadIdx.x == 1023) base = excl + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base;
 }
 inline int ilog2(int x) { int l = 0; while ((1 << l) < x) ++l; return l; }
 // g = dZ * sech^2(enc+pred) reduced over u (d_enc) and over t (d_pred).  Both kernels stream WHOLE rows of the
@@ -523,6 +563,8 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 struct TcScratch {
     __nv_bfloat16 *Wt, *Wb, *dl, *zb, *dz;   // zb rows have stride H+8 (ones column at H); dz is bf16
     float* dWx;                             // (H+8, V) fp32: dW rows, then the db row produced by the ones column
+    int* slot;                              // tile -> compact row block (per backward chunk)
+    int* count;                             // number of valid tiles of the chunk
     int bchunk;          // utterances per backward pass
     size_t rows_chunk;   // bchunk * tiles_per_utt * 128
     size_t bytes;
@@ -546,6 +588,8 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * (d.H + 8) * 2));
     s.dz = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
     s.dWx = reinterpret_cast<float*>(take((size_t)(d.H + 8) * d.V * 4));
+    s.slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
+    s.count = reinterpret_cast<int*>(take(256));
     s.bytes = (size_t)(p - static_cast<char*>(base));
     return s;
 }
@@ -681,6 +725,13 @@ inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, con
 
 namespace rb {
 
+// pinned host word for the valid-tile count read-back (compacted backward)
+inline int* host_count() {
+    static int* h = nullptr;
+    if (!h && cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocDefault) != cudaSuccess) h = nullptr;
+    return h;
+}
+
 // Library-owned side stream for the fork/join inside the backward (created once per process).
 struct SideStream {
     cudaStream_t stream = nullptr;
@@ -700,7 +751,7 @@ inline SideStream& side_stream() {
 inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                 const float* W, const float* bias, const int* labels, const int* ylen,
                                 const int* xlen, const float* lse, const float4* coef, float* d_enc, float* d_pred,
-                                float* dW, float* db, cudaStream_t s, unsigned* launches) {
+                                float* dW, float* db, cudaStream_t s, unsigned* launches, bool compact) {
     (void)W; (void)lse;
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     if (!g.ok) return tc_unsupported(d);
@@ -710,8 +761,26 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         JointTcParams p;
         tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
         p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb; p.zld = d.H + 8;
-        const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU)};
-        const size_t rows = (size_t)nb * g.nTb * g.nUb * 128;
+        const int ntiles = nb * g.nTb * g.nUb;
+        size_t rows = (size_t)ntiles * 128;
+        const int* slot = nullptr;
+        if (compact) {
+            // Ragged batches: only tiles that intersect the valid lattice get rows in dl / zb / dZ, so the two GEMMs
+            // run over the valid rows instead of the padded ones.  Their row count must be known on the HOST: one
+            // 4-byte read-back + stream synchronise per chunk (before anything of this chunk is enqueued, so the
+            // GPU only idles for the launch latency).  Off by default in the C ABI (host_sync_ok == 0).
+            tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count);
+            int* hcount = host_count();
+            if (!hcount || cudaMemcpyAsync(hcount, sc.count, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                cudaStreamSynchronize(s) != cudaSuccess)
+                return RNNT_STATUS_EXECUTION_FAILED;
+            rows = (size_t)(*hcount) * 128;
+            slot = sc.slot;
+            *launches += 1;
+            if (rows == 0) continue;
+        }
+        p.slot = slot;
+        const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU), slot};
         rnntStatus_t st = tc_dispatch<1>(d, g, sc, p, s);
         if (st) return st;
         zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, d.H + 8);

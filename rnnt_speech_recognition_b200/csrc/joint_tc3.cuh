@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             const TileInfo ti = decode_tile(p, tile);
             if (p.dbg & 8) continue;
             if (!ti.valid) {
-                if (MODE == 1) {  // the plain GEMMs reduce over ALL rows: padding tiles must read as zero
+                if (MODE == 1 && !p.slot) {  // uncompacted rows: the plain GEMMs reduce over ALL rows, padding tiles must read as zero
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
                     uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
                     for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 }
                 continue;
             }
+            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
             const int tl = r2 / p.UU, ul = r2 % p.UU;   // row of the enc box / of the pred box
             const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
             for (int kb = 0; kb < KB; ++kb) {
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
                 if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
                 if (MODE == 1 && p.zb) {
-                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + r2) * p.zld + kb * 64 + hh * 32);
+                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + (rowbase + r2) * p.zld + kb * 64 + hh * 32);
                     zdst[0] = make_uint4(zr[0], zr[1], zr[2], zr[3]);   zdst[1] = make_uint4(zr[4], zr[5], zr[6], zr[7]);
                     zdst[2] = make_uint4(zr[8], zr[9], zr[10], zr[11]); zdst[3] = make_uint4(zr[12], zr[13], zr[14], zr[15]);
                 }
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
             if (!ti.valid) continue;
+            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
             const int r = warp * 32 + lane;
             const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
             const bool rv = t < ti.Tn && u < ti.Un;
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 #pragma unroll
                         for (int i = 0; i < 32; i += 2)
                             o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
-                        uint4* dst = reinterpret_cast<uint4*>(p.dl + ((size_t)tile * 128 + r) * p.V + col0);
+                        uint4* dst = reinterpret_cast<uint4*>(p.dl + (rowbase + r) * p.V + col0);
                         dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
                         dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
                         dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
             }
             if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
-                __nv_bfloat16* drow = p.dl + ((size_t)tile * 128 + r) * p.V;
+                __nv_bfloat16* drow = p.dl + (rowbase + r) * p.V;
                 drow[p.blank] = __float2bfloat16(csb);
                 if (lab >= 0) drow[lab] = __float2bfloat16(csl);
             }

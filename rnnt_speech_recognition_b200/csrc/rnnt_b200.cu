@@ -381,7 +381,7 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
     if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     unsigned nl = 0;
     rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, W, bias, labels, label_lengths, input_lengths,
-                                      ws.loss.lse, ws.coef, d_enc, d_pred, dW, db, s, &nl);
+                                      ws.loss.lse, ws.coef, d_enc, d_pred, dW, db, s, &nl, d.allow_host_sync != 0);
     RB_LAUNCHED(nl);
     return st;
 #else

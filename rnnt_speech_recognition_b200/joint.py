@@ -11,6 +11,7 @@ Reference being replaced (file:line under /root/reference):
 reference never exist here, in either direction.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -26,9 +27,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _desc(B, T, U, H, V, blank, precision):
+def _desc(B, T, U, H, V, blank, precision, compact=True):
+    # torch callers synchronise with the host every step anyway (loss read-back), so the torch surface lets the
+    # backward compact ragged batches (one 4-byte read-back); capture-safe callers pass compact=False.
+    sync_ok = 1 if (compact and os.environ.get("RNNTB200_COMPACT", "1") != "0"
+                    and not torch.cuda.is_current_stream_capturing()) else 0
     return _lib.JointDesc(B, T, U, H, V, int(blank), _PREC[precision],
-                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value)
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, sync_ok)
 
 
 def _workspace(desc, device):
@@ -62,7 +67,7 @@ def _check(enc, pred, W, b, labels, input_lengths, label_lengths):
 
 class _JointRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision):
+    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision, compact):
         L = _lib.load()
         enc, pred, W, b = (t.contiguous() for t in (enc, pred, W, b))
         labels, input_lengths, label_lengths = (t.contiguous() for t in (labels, input_lengths, label_lengths))
@@ -71,14 +76,14 @@ class _JointRNNT(torch.autograd.Function):
         U, V = pred.shape[1], W.shape[1]
         lab = labels if labels.numel() else torch.zeros(1, dtype=torch.int32, device=enc.device)
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, blank, precision)
+            desc = _desc(B, T, U, H, V, blank, precision, compact)
             ws = _workspace(desc, enc.device)
             costs = torch.empty(B, dtype=torch.float32, device=enc.device)
             st = L.rnntb200_joint_loss_forward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                _ptr(label_lengths), _ptr(input_lengths), _ptr(costs), _ptr(ws))
         _lib.check(st, "rnntb200_joint_loss_forward")
         ctx.save_for_backward(enc, pred, W, b, lab, input_lengths, label_lengths)
-        ctx.ws, ctx.dims, ctx.blank, ctx.precision = ws, (B, T, U, H, V), blank, precision
+        ctx.ws, ctx.dims, ctx.blank, ctx.precision, ctx.compact = ws, (B, T, U, H, V), blank, precision, compact
         return costs
 
     @staticmethod
@@ -89,20 +94,23 @@ class _JointRNNT(torch.autograd.Function):
         g = grad_costs.to(torch.float32).contiguous()
         d_enc, d_pred, dW, db = (torch.empty_like(t) for t in (enc, pred, W, b))
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision)
+            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.compact)
             st = L.rnntb200_joint_loss_backward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                 _ptr(label_lengths), _ptr(input_lengths), _ptr(g), _ptr(d_enc),
                                                 _ptr(d_pred), _ptr(dW), _ptr(db), _ptr(ctx.ws))
         _lib.check(st, "rnntb200_joint_loss_backward")
         ctx.ws = None
-        return d_enc, d_pred, dW, db, None, None, None, None, None
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None
 
 
-def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank=0, precision="bf16"):
+def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank=0, precision="bf16",
+                    compact=True):
     """Per-utterance RNN-T NLL (B,) of logits = tanh(enc_acts[:,:,None]+pred_acts[:,None]) @ W + b,
     differentiable w.r.t. enc_acts, pred_acts, W, b -- without ever materialising (B,T,U,V).
-    precision: 'bf16' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (exact CUDA-core path)."""
-    return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision)
+    precision: 'bf16' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (exact CUDA-core path).
+    compact: let the bf16 backward skip padding tiles of ragged batches (one 4-byte host read-back per chunk);
+    pass False for a fully sync-free (CUDA-graph capturable) call."""
+    return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact)
 
 
 def joint_logits(enc_acts, pred_acts, W, b):

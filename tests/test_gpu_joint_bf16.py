@@ -86,3 +86,14 @@ def test_bf16_edge_lattices(oracle, B, T, U, V, H, blank):
     assert_close(costs, o["costs"], rtol=BF16_COST_RTOL, atol=1e-2, what="costs")
     for g, n in zip(grads, ("d_enc", "d_pred", "dW", "db")):
         assert_close(g, o[n], rtol=0, atol=0, ntol=BF16_GRAD_NTOL, what=n)
+
+
+def test_compacted_and_padded_backward_agree():
+    """Ragged batch: the backward over valid tiles only (allow_host_sync) and the sync-free backward over the padded
+    tile set produce the same gradients (identical arithmetic per row; only the GEMM reduction order may differ)."""
+    k = synth(5, 70, 45, 256, 192, 31, ragged=True)
+    c1, g1 = run_joint(k, "bf16", compact=True)
+    c2, g2 = run_joint(k, "bf16", compact=False)
+    assert np.array_equal(c1, c2)
+    for a, b_, n in zip(g1, g2, ("d_enc", "d_pred", "dW", "db")):
+        assert_close(a, b_, rtol=1e-5, atol=0, ntol=1e-5, what=n)
