@@ -471,6 +471,105 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     }
 }
 
+// Faster fp32 GEMM for the exact path: 128x128x8 tiles, 256 threads, 8x8 register micro-tiles (as 2x2 blocks of
+// 4x4 so that every smem read is a conflict-free float4), 16-byte global loads along whichever dimension is
+// contiguous.  Requirements (checked by the launcher, else sgemm_kernel is used): the contiguous dimension of each
+// operand is a multiple of 4 and 16-byte aligned.  Same semantics as sgemm_kernel.
+template <bool A_K_CONTIG, bool B_N_CONTIG>
+__global__ void __launch_bounds__(256) sgemm128_kernel(const float* __restrict__ A, const float* __restrict__ Bm,
+                                                       float* __restrict__ C, const float* __restrict__ bias, int M,
+                                                       int N, int K, long long sAm, long long sAk, long long sBk,
+                                                       long long sBn, long long ldc, int accumulate) {
+    constexpr int BM = 128, BN = 128, BK = 8;
+    __shared__ __align__(16) float As[2][BK][BM];
+    __shared__ __align__(16) float Bs[2][BK][BN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int tx = tid & 15, ty = tid >> 4;
+    // split-K: blockIdx.z owns K range [kbeg, kend); partial products are combined with atomicAdd (accumulate != 0)
+    const int kchunk = ((K + (int)gridDim.z - 1) / (int)gridDim.z + BK - 1) / BK * BK;
+    const int kbeg = blockIdx.z * kchunk, kend = min(K, kbeg + kchunk);
+    if (kbeg >= kend) return;
+    float acc[8][8] = {};
+    float4 ra, rb;
+    auto gload = [&](int k0) {
+        if (A_K_CONTIG) {   // one float4 along k: row m = tid/2, k4 = (tid&1)*4
+            const int m = m0 + (tid >> 1), k = k0 + (tid & 1) * 4;
+            ra = (m < M && k < K) ? *reinterpret_cast<const float4*>(A + m * sAm + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {            // one float4 along m: k = tid/32, m4 = (tid&31)*4
+            const int k = k0 + (tid >> 5), m = m0 + (tid & 31) * 4;
+            ra = (m < M && k < K) ? *reinterpret_cast<const float4*>(A + k * sAk + m) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (B_N_CONTIG) {
+            const int k = k0 + (tid >> 5), n = n0 + (tid & 31) * 4;
+            rb = (n < N && k < K) ? *reinterpret_cast<const float4*>(Bm + k * sBk + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+            const int n = n0 + (tid >> 1), k = k0 + (tid & 1) * 4;
+            rb = (n < N && k < K) ? *reinterpret_cast<const float4*>(Bm + n * sBn + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    auto sstore = [&](int buf) {
+        if (A_K_CONTIG) {
+            const int m = tid >> 1, k = (tid & 1) * 4;
+            As[buf][k][m] = ra.x; As[buf][k + 1][m] = ra.y; As[buf][k + 2][m] = ra.z; As[buf][k + 3][m] = ra.w;
+        } else {
+            *reinterpret_cast<float4*>(&As[buf][tid >> 5][(tid & 31) * 4]) = ra;
+        }
+        if (B_N_CONTIG) {
+            *reinterpret_cast<float4*>(&Bs[buf][tid >> 5][(tid & 31) * 4]) = rb;
+        } else {
+            const int n = tid >> 1, k = (tid & 1) * 4;
+            Bs[buf][k][n] = rb.x; Bs[buf][k + 1][n] = rb.y; Bs[buf][k + 2][n] = rb.z; Bs[buf][k + 3][n] = rb.w;
+        }
+    };
+    K = kend;                      // the guards in gload() compare against the end of this block's K range
+    gload(kbeg);
+    sstore(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = kbeg; k0 < K; k0 += BK) {
+        if (k0 + BK < K) gload(k0 + BK);
+#pragma unroll
+        for (int k = 0; k < BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (k0 + BK < K) {
+            sstore(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int gm = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + i - 4);
+        if (gm >= M) continue;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const int gn = n0 + jj * 64 + tx * 4;
+            if (gn >= N) continue;   // N % 4 == 0: a float4 is either fully inside or fully outside
+            float4 v = make_float4(acc[i][jj * 4], acc[i][jj * 4 + 1], acc[i][jj * 4 + 2], acc[i][jj * 4 + 3]);
+            if (bias && blockIdx.z == 0) { const float4 bb = *reinterpret_cast<const float4*>(bias + gn); v.x += bb.x; v.y += bb.y; v.z += bb.z; v.w += bb.w; }
+            float* cp = C + (long long)gm * ldc + gn;
+            if (gridDim.z > 1) {   // split-K: C was zero-initialised (or holds earlier chunks); bias added by split 0 only
+                atomicAdd(cp, v.x); atomicAdd(cp + 1, v.y); atomicAdd(cp + 2, v.z); atomicAdd(cp + 3, v.w);
+            } else {
+                float4* c = reinterpret_cast<float4*>(cp);
+                if (accumulate) { const float4 o = *c; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+                *c = v;
+            }
+        }
+    }
+}
+
 // dpre = dz * (1 - z^2); d_enc[b,t,:] += sum_u dpre, d_pred[b,u,:] += sum_t dpre (atomics; exact path only)
 __global__ void __launch_bounds__(256) dz_reduce_kernel(const float* __restrict__ dz, const float* __restrict__ z,
                                                         long long row0, long long nrows, int maxT, int maxU, int H,

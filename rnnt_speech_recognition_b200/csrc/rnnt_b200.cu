@@ -183,11 +183,36 @@ inline unsigned ew_blocks(long long total) {
     return (unsigned)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
 }
 
+// C[M,N] (+)= A.B with generic strides; picks the 128x128 float4 kernel when alignment allows
+template <bool AK, bool BN_>
+void launch_sgemm(const float* A, const float* Bm, float* C, const float* bias, int M, int N, int K, long long sAm,
+                  long long sAk, long long sBk, long long sBn, long long ldc, int accumulate, cudaStream_t s) {
+    auto al16 = [](const void* p) { return ((uintptr_t)p % 16) == 0; };
+    const bool a_ok = AK ? (K % 4 == 0 && sAm % 4 == 0) : (M % 4 == 0 && sAk % 4 == 0);
+    const bool b_ok = BN_ ? (N % 4 == 0 && sBk % 4 == 0) : (K % 4 == 0 && sBn % 4 == 0);
+    const bool fast = a_ok && b_ok && N % 4 == 0 && ldc % 4 == 0 && al16(A) && al16(Bm) && al16(C) && (!bias || al16(bias));
+    if (fast) {
+        // few output tiles but a long K (dW = Z^T.dL): split K over blockIdx.z so the grid fills the 148 SMs;
+        // only for accumulating calls, whose output already holds valid data to atomically add into
+        int splits = 1;
+        const int tiles = ((N + 127) / 128) * ((M + 127) / 128);
+        if (accumulate && tiles < 148 && K >= 4096) {
+            splits = (148 * 4 + tiles - 1) / tiles;
+            if (splits > K / 512) splits = K / 512;
+            if (splits < 1) splits = 1;
+        }
+        dim3 grid((N + 127) / 128, (unsigned)((M + 127) / 128), splits);
+        rb::sgemm128_kernel<AK, BN_><<<grid, 256, 0, s>>>(A, Bm, C, bias, M, N, K, sAm, sAk, sBk, sBn, ldc, accumulate);
+    } else {
+        dim3 grid((N + 63) / 64, (unsigned)((M + 63) / 64));
+        rb::sgemm_kernel<AK, BN_><<<grid, 256, 0, s>>>(A, Bm, C, bias, M, N, K, sAm, sAk, sBk, sBn, ldc, accumulate);
+    }
+    RB_LAUNCHED(1);
+}
 void launch_sgemm_zw(const float* Z, const float* W, const float* bias, float* L, long long rows, int H, int V,
                      cudaStream_t s) {
-    dim3 grid((V + 63) / 64, (unsigned)((rows + 63) / 64));
-    rb::sgemm_kernel<true, true><<<grid, 256, 0, s>>>(Z, W, L, bias, (int)rows, V, H, H, 1, V, 1, V, 0);
-    RB_LAUNCHED(1);
+    rb::ScopedTimer tm("sgemm L=Z.W+b", s);
+    launch_sgemm<true, true>(Z, W, L, bias, (int)rows, V, H, H, 1, V, 1, V, 0, s);
 }
 
 rnntStatus_t exact_forward(const rnntb200JointDesc& d, const JointWs& ws, const float* enc, const float* pred,
@@ -233,24 +258,22 @@ rnntStatus_t exact_backward(const rnntb200JointDesc& d, const JointWs& ws, const
             ws.loss.betas, ws.loss.llf, grad_costs);
         // dZ = dL . W^T      (rows x V) . (V x H):  B(k=v, n=h) = W[h*V + v]
         {
-            dim3 grid((d.H + 63) / 64, (unsigned)((rows + 63) / 64));
-            rb::sgemm_kernel<true, false><<<grid, 256, 0, s>>>(L, W, dZ, nullptr, (int)rows, d.H, d.V, d.V, 1, 1, d.V,
-                                                               d.H, 0);
+            rb::ScopedTimer tm("sgemm dZ=dL.W^T", s);
+            launch_sgemm<true, false>(L, W, dZ, nullptr, (int)rows, d.H, d.V, d.V, 1, 1, d.V, d.H, 0, s);
         }
         rb::dz_reduce_kernel<<<ew_blocks(rows * d.H), 256, 0, s>>>(dZ, Z, r0, rows, d.maxT, d.maxU, d.H, d_enc,
                                                                    d_pred);
         // dW += Z^T . dL     (H x rows) . (rows x V):  A(m=h, k=r) = Z[r*H + h]
         {
-            dim3 grid((d.V + 63) / 64, (d.H + 63) / 64);
-            rb::sgemm_kernel<false, true><<<grid, 256, 0, s>>>(Z, L, dW, nullptr, d.H, d.V, (int)rows, 1, d.H, d.V, 1,
-                                                               d.V, 1);
+            rb::ScopedTimer tm("sgemm dW+=Z^T.dL", s);
+            launch_sgemm<false, true>(Z, L, dW, nullptr, d.H, d.V, (int)rows, 1, d.H, d.V, 1, d.V, 1, s);
         }
         {
             long long gy = (rows + 255) / 256;
             if (gy > 512) gy = 512;
             rb::colsum_kernel<<<dim3((d.V + 31) / 32, (unsigned)gy), 256, 0, s>>>(L, rows, d.V, db);
         }
-        RB_LAUNCHED(7);
+        RB_LAUNCHED(5);
         if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     }
     return RNNT_STATUS_SUCCESS;
