@@ -108,7 +108,7 @@ rnntStatus_t compute_rnnt_loss_fp64(const double* const activations, double* gra
  * Part 2 -- B200 additions (no reference analogue; conventions as above)
  * ------------------------------------------------------------------------------------------ */
 
-/** compute_rnnt_loss with DEVICE costs and no host synchronisation (graph-capturable).  This is
+/** compute_rnnt_loss with DEVICE costs and no host synchronisation.  This is
  *  what the torch surface calls; replaces the D2H + cudaStreamSynchronize of gpu_rnnt.h:209-213.
  *  grad_scale: optional DEVICE float (B); when non-NULL gradients[b] are pre-multiplied by it
  *  (folds _RNNTLossGrad's grad_loss[:,None,None,None]*grads, warprnnt_tensorflow/__init__.py:37-42). */
@@ -132,7 +132,7 @@ typedef struct {
     int blank_label;
     int precision; /* rnntb200Precision */
     CUstream stream;
-    /** 0 (default): the library never synchronises with the host (graph-capturable).  1: the bf16 backward may read
+    /** 0 (default): the library never synchronises with the host.  1: the bf16 backward may read
      *  ONE int (the number of lattice tiles that intersect the valid region) back per utterance chunk, so that
      *  ragged batches run their GEMMs over the valid rows only instead of the padded lattice. */
     int allow_host_sync;

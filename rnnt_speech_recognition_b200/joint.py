@@ -109,7 +109,7 @@ def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_leng
     differentiable w.r.t. enc_acts, pred_acts, W, b -- without ever materialising (B,T,U,V).
     precision: 'bf16' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (exact CUDA-core path).
     compact: let the bf16 backward skip padding tiles of ragged batches (one 4-byte host read-back per chunk);
-    pass False for a fully sync-free (CUDA-graph capturable) call."""
+    pass False for a fully sync-free call (stream capture of the whole step is not validated yet, tools/graph_capture.py)."""
     return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact)
 
 
