@@ -127,12 +127,17 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             if (!decode_tile(p, tile).valid) continue;
             for (int c = 0; c < NCH; ++c, ++g) {
                 const uint32_t buf = g % NBUF, use = g / NBUF;
-                ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
-                ptx::tc_fence_after();
+                if (!(p.dbg & 128)) {
+                    ptx::mbar_wait(&acc_empty[buf], (use & 1) ^ 1);
+                    ptx::tc_fence_after();
+                }
                 const uint32_t d_tmem = acc0 + buf * NC;
                 for (int kb0 = 0; kb0 < KB; kb0 += KS) {
                     if (!(p.dbg & 4)) ptx::mbar_wait(&w_full[stage], phase);
-                    ptx::tc_fence_after();   // once per stage (4*KS MMAs)
+                    // TMA-written smem is consumed by the same (async) proxy the MMA reads through: the mbarrier wait
+                    // alone orders it.  tcgen05.fence::after_thread_sync is only needed where OTHER THREADS' tcgen05
+                    // traffic is involved: after acc_empty (epilogue tcgen05.ld) and z_full (producer tcgen05.st).
+                    if (p.dbg & 64) ptx::tc_fence_after();
                     const uint64_t bdesc0 = ptx::umma_desc_k_sw128(ptx::smem_u32(wsm + (size_t)stage * stage_bytes));
                     const uint32_t a_st = tmem_base + (uint32_t)kb0 * 32;
                     if (c == 0 && !(p.dbg & 8)) {
@@ -149,8 +154,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                             __syncwarp();
                         }
                     } else {
-                        // steady state: the whole stage (up to 20 MMAs) from ONE elected block with immediate
-                        // operand offsets.  A per-K-block loop cost ~40 cycles of issue overhead per 46-cycle MMA.
+                        // steady state: the whole stage (up to 20 MMAs) AND its commits from ONE elected block with
+                        // immediate operand offsets.  The single issuing thread is the pace-setter at N=64 (the probe
+                        // reaches the 32-cycle floor only with >= 20 MMAs per block), so nothing else goes in between.
                         if (ptx::elect_one()) {
 #pragma unroll
                             for (int i = 0; i < 5; ++i) {
@@ -162,8 +168,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                                                           (i | k) ? 1u : (uint32_t)(kb0 != 0));
                                 }
                             }
+                            if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
+                            if (kb0 + KS >= KB) ptx::umma_commit(&acc_full[buf]);
                         }
                         __syncwarp();
+                        if (++stage == stages) { stage = 0; phase ^= 1; }
+                        continue;
                     }
                     if (ptx::elect_one()) {
                         if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
@@ -264,6 +274,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 ptx::tc_fence_after();
 #pragma unroll
                 for (int j = 0; j < NC / 32; ++j) {
+                    if (p.dbg & 256) continue;
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(lane_addr + buf * NC + j * 32, v);
                     ptx::tmem_ld_wait();
