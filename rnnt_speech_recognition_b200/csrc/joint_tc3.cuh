@@ -221,10 +221,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 for (int c = 0; c < 8; ++c) {
                     const float4 q = *reinterpret_cast<const float4*>(prow + ((c ^ (ul & 7)) << 4));
                     const float4 e = *reinterpret_cast<const float4*>(erow + (c << 4));
-                    if (ok && (p.dbg & 32)) {          // experiment: packed bf16x2 tanh (half the MUFU issues)
-                        zr[c * 2 + 0] = ptx::tanh_bf16x2(e.x + q.x, e.y + q.y);
-                        zr[c * 2 + 1] = ptx::tanh_bf16x2(e.z + q.z, e.w + q.w);
-                    } else if (ok) {
+                    if (ok) {   // (tanh.approx.bf16x2 / f16x2 lower to two scalar MUFU ops on sm_100a: no gain from packing)
                         zr[c * 2 + 0] = ptx::pack_bf16x2(ptx::tanh_approx(e.x + q.x), ptx::tanh_approx(e.y + q.y));
                         zr[c * 2 + 1] = ptx::pack_bf16x2(ptx::tanh_approx(e.z + q.z), ptx::tanh_approx(e.w + q.w));
                     } else {

@@ -167,12 +167,6 @@ __device__ __forceinline__ float tanh_approx(float x) {
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-// two tanh per MUFU issue: inputs rounded to bf16 first, result is the packed bf16 pair (lo -> bits [0,16))
-__device__ __forceinline__ uint32_t tanh_bf16x2(float lo, float hi) {
-    uint32_t r;
-    asm("{\n.reg .b32 t;\ncvt.rn.bf16x2.f32 t, %2, %1;\ntanh.approx.bf16x2 %0, t;\n}" : "=r"(r) : "f"(lo), "f"(hi));
-    return r;
-}
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
