@@ -62,6 +62,7 @@ def main():
         print("%-6s max|diff| %.4g  mean %.4g  (ref max %.4g)  nan %d" % (n, d.max().item(), d.mean().item(),
               p0[n].abs().max().item(), torch.isnan(p1[n]).sum().item()))
     lse0, lse1 = p0["lse"].view(B, T, U), p1["lse"].view(B, T, U)
+    print("lse signed mean (bf16-fp32) %.4g std %.4g" % ((lse1 - lse0).mean().item(), (lse1 - lse0).std().item()))
     print("lse fp32 [0,0,:8]", lse0[0, 0, :8].tolist())
     print("lse bf16 [0,0,:8]", lse1[0, 0, :8].tolist())
     SK = (T + U - 1) * U
@@ -72,7 +73,8 @@ def main():
             for u in range(U if n == "lpb" else U - 1):
                 mask[:, t + u, u] = True
         d = (a0 - a1).abs()[mask]
-        print("%-6s max|diff| %.4g mean %.4g" % (n, d.max().item(), d.mean().item()))
+        sd = (a1 - a0)[mask]
+        print("%-6s max|diff| %.4g mean|diff| %.4g  signed mean (bf16-fp32) %.4g  std %.4g" % (n, d.max().item(), d.mean().item(), sd.mean().item(), sd.std().item()))
     for n, a, bb in zip(("d_enc", "d_pred", "dW", "db"), g0, g1):
         d = (a - bb).abs()
         print("%-6s max|diff| %.4g  ref max %.4g  rel-fro %.4g nan %d" % (n, d.max().item(), a.abs().max().item(),
