@@ -155,6 +155,12 @@ class Joint(torch.nn.Module):
         enc_acts, pred_acts = self.hoist(inp_enc, pred_outputs)
         return joint_logits(enc_acts, pred_acts, self.kernel_2, self.bias_2)
 
+    def step(self, f, g):
+        """Greedy-decode joint, utils/decoding.py:6-18: ``joint(model, f, g)`` adds ``f`` (B,T,P) to the LAST
+        prediction-network frame ``g[:, -1, :]`` and returns ``outputs[:, 0, 0, :]`` -- the (B,V) logits of frame 0."""
+        enc_acts, pred_acts = self.hoist(f[:, :1, :], g[:, -1:, :])
+        return joint_logits(enc_acts, pred_acts, self.kernel_2, self.bias_2)[:, 0, 0, :]
+
     def loss(self, inp_enc, pred_outputs, labels, input_lengths, label_lengths):
         enc_acts, pred_acts = self.hoist(inp_enc, pred_outputs)
         return joint_rnnt_loss(enc_acts, pred_acts, self.kernel_2, self.bias_2, labels, input_lengths, label_lengths,

@@ -76,3 +76,26 @@ def test_fused_equals_op_on_materialised_logits():
     for g, x, n in zip(grads, t, ("d_enc", "d_pred", "dW", "db")):
         assert_close(g, x.grad.cpu().numpy(), rtol=1e-4, atol=1e-6, ntol=2e-5, what=n)
     assert abs(grads[3].sum()) < 1e-3 * np.abs(grads[3]).sum() + 1e-5     # sum_v db == 0 (rows of dlogits sum to 0)
+
+
+def test_joint_module_forward_and_decode_step():
+    """Joint.forward == model.py:158-166 literally (un-hoisted Dense-1), Joint.step == utils/decoding.py:6-18."""
+    import rnnt_speech_recognition_b200 as rb
+    torch.manual_seed(3)
+    j = rb.Joint(proj_size=48, joint_net_size=64, vocab_size=40, precision="fp32").cuda()
+    f, g = torch.randn(2, 7, 48, device="cuda"), torch.randn(2, 5, 48, device="cuda")
+    with torch.no_grad():
+        want = torch.tanh((f[:, :, None] + g[:, None]) @ j.kernel_1 + j.bias_1) @ j.kernel_2 + j.bias_2
+        got = j(f, g)
+        assert torch.allclose(got, want, atol=2e-5, rtol=1e-5)
+        step = j.step(f, g)
+        want_step = (torch.tanh((f[:, :, None] + g[:, -1:, :][:, None]) @ j.kernel_1 + j.bias_1) @ j.kernel_2 + j.bias_2)[:, 0, 0, :]
+        assert step.shape == (2, 40) and torch.allclose(step, want_step, atol=2e-5, rtol=1e-5)
+    # fused loss through the module: gradients reach the Keras-layout parameters of both Dense layers
+    lab = torch.randint(1, 40, (2, 4), dtype=torch.int32, device="cuda")
+    il, ll = torch.tensor([7, 5], dtype=torch.int32, device="cuda"), torch.tensor([4, 2], dtype=torch.int32, device="cuda")
+    costs = j.loss(f, g, lab, il, ll)
+    costs.sum().backward()
+    ref = rb.rnnt_loss(torch.tanh((f[:, :, None] + g[:, None]) @ j.kernel_1 + j.bias_1) @ j.kernel_2 + j.bias_2, lab, il, ll)
+    assert torch.allclose(costs, ref, rtol=1e-5, atol=1e-4)
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in j.parameters())
