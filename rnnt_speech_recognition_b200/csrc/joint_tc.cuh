@@ -1,4 +1,8 @@
-// joint_tc.cuh -- bf16 tensor-core (tcgen05 / TMEM / TMA) kernels of the fused joint + loss path.
+// joint_tc.cuh -- bf16 tensor-core (tcgen05 / TMEM / TMA) path of the fused joint + loss: shared definitions
+// (tile geometry, kernel parameters, tensor maps, scratch layout), the FIRST-generation kernel, the backward's
+// reduction kernels and the host-side orchestration (tc_forward / tc_backward / tc_dispatch).
+// The default kernel is joint_tc3_kernel (joint_tc3.cuh); joint_tc_kernel below is generation 1
+// (RNNTB200_TC_VARIANT=1), also the fallback when z does not fit tensor memory (H > 768).
 //
 // joint_tc_kernel<MODE>: one persistent CTA per SM, each looping over 128-cell lattice tiles
 // (TT time steps x UU label positions of one utterance).  Per tile:
@@ -11,8 +15,9 @@
 //       MODE 0 (forward):  add bias, ONLINE log-sum-exp across the V chunks, pick logit[blank] and
 //                          logit[label_u]  ->  lse (natural order), lp_blank / lp_label (skewed planes)
 //                          -- the (B,T,U,V) logits of model.py:165-166 never reach HBM;
-//       MODE 1 (backward): dlogit = g*exp(x + kd) - [blank] g*sb - [label] g*sl  (coefficients from
-//                          cell_coef_kernel) -> bf16 rows of the dlogits workspace (+ bf16 z rows).
+//       MODE 1 (backward): dlogit = g*exp(x + kd) for all columns, then the blank / label entries are overwritten
+//                          with the values cell_coef_kernel precomputed -> bf16 rows of the dlogits workspace
+//                          (+ the bf16 z rows the dW GEMM consumes).
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
