@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO = os.path.join(HERE, "librnnt_b200.so")
+SO = os.environ.get("RNNTB200_LIB") or os.path.join(HERE, "librnnt_b200.so")   # RNNTB200_LIB: A/B another build
 
 RNNT_CPU, RNNT_GPU = 0, 1
 FP32_EXACT, BF16_TC = 0, 1

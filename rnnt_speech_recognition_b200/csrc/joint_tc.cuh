@@ -296,7 +296,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
                         float y[32];
 #pragma unroll
                         for (int i = 0; i < 32; ++i)
-                            y[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bv, i);   // acc already carries log2(e)
+                            y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
                         if (MODE == 0) {
                             float gm = y[0];
 #pragma unroll
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) joint_tc_kernel(const __grid_co
     if (warp == 9) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
-// W (H,V) fp32 -> Wt (V,H) bf16 = (W*log2 e)^T [B operand of the logits GEMM, K=h] and Wb (H,V) bf16 [B operand of dZ, K=v]
+// W (H,V) fp32 -> Wt (V,H) bf16 [B operand of the logits GEMM, K=h] and Wb (H,V) bf16 [B operand of dZ, K=v]
 __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt,
                                                         __nv_bfloat16* __restrict__ Wb, int H, int V) {
     __shared__ float tile[32][33];
@@ -369,8 +369,7 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int v = v0 + i, h = h0 + tx;
-        // W^T carries the log2(e) factor so that the logits GEMM lands directly in the log2 domain of the epilogue
-        if (h < H && v < V) Wt[(size_t)v * H + h] = __float2bfloat16(tile[tx][i] * 1.4426950408889634f);
+        if (h < H && v < V) Wt[(size_t)v * H + h] = __float2bfloat16(tile[tx][i]);
     }
 }
 

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) joint_tc2_kernel(const __grid_
                     float y[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
-                        y[i] = __uint_as_float(v[i]) + __shfl_sync(0xffffffffu, bv, i);   // acc already carries log2(e)
+                        y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
                     if (MODE == 0) {
                         float gm = y[0];
 #pragma unroll

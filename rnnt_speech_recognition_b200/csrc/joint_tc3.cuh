@@ -79,28 +79,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc0 = tmem_base + (uint32_t)KB * 32;  // accumulator region starts after the z columns
     const int ntiles = p.nb * p.nTb * p.nUb;
-    // The accumulators START from the bias (times log2 e; W^T carries the same factor), so the epilogue reads finished
-    // log2-domain logits straight from TMEM: no per-element bias broadcast / scale.  A buffer is re-initialised by the
-    // epilogue warps right after they drained it, with the bias columns of the chunk that will use it next.
-    auto preinit = [&](uint32_t buf, int chunk_col) {   // epilogue warps only: 32 lanes x 64 columns each
-#pragma unroll
-        for (int j = 0; j < NC / 16; ++j) {
-            uint32_t bw[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int col = chunk_col * NC + j * 16 + i;
-                bw[i] = __float_as_uint(bias_in_smem ? bias2[col] : __ldg(p.bias + col) * 1.4426950408889634f);
-            }
-            ptx::tmem_st_32x16(acc0 + ((uint32_t)((threadIdx.x >> 5) * 32) << 16) + buf * NC + j * 16, bw);
-        }
-        ptx::tmem_st_wait();
-    };
-    if ((threadIdx.x >> 5) < 4) {
-        for (int bb = 0; bb < NBUF; ++bb) preinit(bb, bb % NCH);
-        ptx::tc_fence_before();
-    }
-    __syncthreads();
-    ptx::tc_fence_after();
 
     if (warp == 14) {
         // ===================== enc / pred TMA: one K block of the tile's rows per ring stage, runs ahead across tiles
@@ -171,7 +149,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
                                     ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8, bdesc0 + (uint64_t)(i * 512 + k * 2),
-                                                      idesc, 1u);   // accumulators start from the bias
+                                                      idesc, (uint32_t)((kb0 | i | k) != 0));
                             }
                             __syncwarp();
                         }
@@ -187,7 +165,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                                     for (int k = 0; k < 4; ++k)
                                         ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8,
                                                           bdesc0 + (uint64_t)(i * 512 + k * 2), idesc,
-                                                          1u);   // accumulators start from the bias
+                                                          (i | k) ? 1u : (uint32_t)(kb0 != 0));
                                 }
                             }
                             if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
@@ -299,9 +277,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                     ptx::tmem_ld_wait();
                     if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
                     const int col0 = c * NC + j * 32;
+                    const float bv = bias_in_smem ? bias2[col0 + lane] : __ldg(p.bias + col0 + lane) * LOG2E;
                     float y[32];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) y[i] = __uint_as_float(v[i]);   // bias and log2(e) are already in the accumulator
+                    for (int i = 0; i < 32; ++i)
+                        y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
                     if (MODE == 0) {
                         float gm = y[0];
 #pragma unroll
@@ -343,7 +323,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                         dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
                     }
                 }
-                preinit(buf, (c + NBUF) % NCH);   // this buffer is next used by chunk c+NBUF (possibly of the next tile)
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
