@@ -325,7 +325,7 @@ def main():
         N = int((d["il"].long() * (d["ll"].long() + 1)).sum().item())      # valid lattice cells (== B*T*U when not ragged)
         if cfg["precision"] == "bf16":
             flops = 2.0 * N * H * V
-            dom = next((k for k in kernels if k.endswith("<fwd>")), "joint_tc3_kernel<fwd>")
+            dom = next((k for k in kernels if k.endswith("<fwd>") or k.endswith("<fwd+keep>")), "joint_tc3_kernel<fwd+keep>")
             t_dom = kernels.get(dom)
             ach = flops / (t_dom * 1e-3) / 1e12 if t_dom else None
             peak = pk["bf16_tflops_sustained"]

@@ -136,6 +136,14 @@ typedef struct {
      *  ONE int (the number of lattice tiles that intersect the valid region) back per utterance chunk, so that
      *  ragged batches run their GEMMs over the valid rows only instead of the padded lattice. */
     int allow_host_sync;
+    /** 0: the backward recomputes the projection on the tensor cores (nothing but lse / log-prob pairs / alpha /
+     *  beta survives the forward).  1 (bf16 path): the forward also leaves, in the workspace, the softmax numerators
+     *  of every lattice cell as fp16 (2 bytes per logit) and the tanh outputs as bf16; the backward then forms the
+     *  logit gradients with one streaming pass instead of a second projection.  Set it when a backward call will
+     *  follow; it is honoured only when the whole batch fits one workspace chunk, otherwise (and for fp32) ignored.
+     *  Must have the same value in the forward and the backward call.  With allow_host_sync the one-int read-back
+     *  moves from the backward to the start of the forward. */
+    int keep_activations;
 } rnntb200JointDesc;
 
 /** Bytes of device workspace the forward/backward pair needs (pure function of the descriptor). */

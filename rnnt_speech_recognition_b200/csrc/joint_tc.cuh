@@ -21,6 +21,8 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <mutex>
+#include <unordered_map>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -87,12 +89,18 @@ struct JointTcParams {
     long long SK;
     int b0, nb;                 // utterance range of this launch
     const int* slot;            // optional tile -> compact row-block map of this launch (valid tiles only); NULL = tile order
-    int zld;                    // row stride (elements) of zb: H + 8 (the extra 8 columns carry the ones column for db)
+    int zld;                    // row stride (elements) of zb: tc_zld(H) = H + 16 (column H carries the ones column for db; 32-byte aligned rows)
     int nbuf, swap, ks, dbg;    // v2 kernel: TMEM accumulator buffers; bf16-pair order of TMEM A; K-blocks per W stage; bring-up switches
     float* lse; float* lpb; float* lpl;              // MODE 0 outputs
     const float4* coef; __nv_bfloat16* dl; __nv_bfloat16* zb;  // MODE 1: coefficients in, dlogits / z rows out
+    // MODE 2 (forward that KEEPS its activations): dl receives the softmax numerators 2^(y - gm) as fp16 (same rows,
+    // same bytes as the bf16 dlogits that dl_from_kept_kernel later writes over them), gm the running maximum each
+    // 32-column group was taken against, zb the tanh outputs.
+    float* gm;
 };
 
+// zb row pitch: H + 16 elements keeps every row 32-byte aligned (256-bit stores); the dW GEMM reads H + 8 columns of it
+inline int tc_zld(int H) { return H + 16; }
 struct TileInfo { int b, t0, u0, Tn, Un; bool valid; };
 __device__ __forceinline__ TileInfo decode_tile(const JointTcParams& p, int tile) {
     TileInfo ti;
@@ -566,8 +574,9 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 }
 
 struct TcScratch {
-    __nv_bfloat16 *Wt, *Wb, *dl, *zb, *dz;   // zb rows have stride H+8 (ones column at H); dz is bf16
+    __nv_bfloat16 *Wt, *Wb, *dl, *zb, *dz;   // zb rows have stride tc_zld(H) (ones column at H); dz is bf16
     float* dWx;                             // (H+8, V) fp32: dW rows, then the db row produced by the ones column
+    float* gm;                              // (row blocks, V/32, 128) fp32: running maxima of the kept numerators (keep_activations)
     int* slot;                              // tile -> compact row block (per backward chunk)
     int* count;                             // number of valid tiles of the chunk
     int bchunk;          // utterances per backward pass
@@ -578,7 +587,7 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     TcScratch s{};
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
-    const size_t per_row = (size_t)d.V * 2 + (size_t)(d.H + 8) * 2 + (size_t)d.H * 2;
+    const size_t per_row = (size_t)d.V * 2 + (size_t)tc_zld(d.H) * 2 + (size_t)d.H * 2 + (size_t)(d.V / 32) * 4;
     const size_t budget = (size_t)16 << 30;
     size_t bc = budget / (rows_utt * per_row);
     if (bc < 1) bc = 1;
@@ -590,8 +599,9 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.Wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.dl = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.V * 2));
-    s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * (d.H + 8) * 2));
+    s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * tc_zld(d.H) * 2));
     s.dz = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
+    s.gm = reinterpret_cast<float*>(take(s.rows_chunk * (size_t)(d.V / 32) * 4));
     s.dWx = reinterpret_cast<float*>(take((size_t)(d.H + 8) * d.V * 4));
     s.slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
     s.count = reinterpret_cast<int*>(take(256));
@@ -675,22 +685,6 @@ template <int MODE>
 inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, const TcScratch& sc, JointTcParams& p,
                                 cudaStream_t s);
 
-inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
-                               const float* W, const float* bias, const int* labels, const int* ylen,
-                               const int* xlen, float* lse, float* lpb, float* lpl, cudaStream_t s,
-                               unsigned* launches) {
-    const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
-    if (!g.ok) return tc_unsupported(d);
-    TcScratch sc = tc_scratch_layout(d, scratch);
-    convert_w_kernel<<<dim3((d.V + 31) / 32, (d.H + 31) / 32), 256, 0, s>>>(W, sc.Wt, sc.Wb, d.H, d.V);
-    JointTcParams p;
-    tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
-    p.b0 = 0; p.nb = d.B;
-    p.lse = lse; p.lpb = lpb; p.lpl = lpl;
-    *launches += 2;
-    return tc_dispatch<0>(d, g, sc, p, s);
-}
-
 }  // namespace rb
 
 #include "bwd_gemm.cuh"
@@ -730,11 +724,77 @@ inline rnntStatus_t tc_dispatch(const rnntb200JointDesc& d, const TcGeom& g, con
 
 namespace rb {
 
-// pinned host word for the valid-tile count read-back (compacted backward)
+// pinned host word for the valid-tile count read-back (ragged batches)
 inline int* host_count() {
     static int* h = nullptr;
     if (!h && cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(int), cudaHostAllocDefault) != cudaSuccess) h = nullptr;
     return h;
+}
+// slot[] / count of the tiles [b0, b0+nb) that intersect the valid lattice; returns the valid ROWS (or -1).  One 4-byte
+// read-back + stream synchronise (before anything that depends on it is enqueued, so the GPU only idles for the
+// launch latency).  Only used when the descriptor allows host synchronisation.
+inline long long compact_tiles(const TcGeom& g, const TcScratch& sc, const int* xlen, const int* ylen, int b0, int ntiles,
+                               cudaStream_t s) {
+    tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count);
+    int* hcount = host_count();
+    if (!hcount || cudaMemcpyAsync(hcount, sc.count, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+        return -1;
+    return (long long)(*hcount) * 128;
+}
+
+// keep_activations: honoured when the generation-3 kernel runs and the whole batch is one workspace chunk
+// (RNNTB200_KEEP=0 turns it off for A/B measurements).
+inline bool tc_keep(const rnntb200JointDesc& d, const TcScratch& sc) {
+    static int env = -1;
+    if (env < 0) { const char* e = getenv("RNNTB200_KEEP"); env = e ? atoi(e) : 1; }
+    return d.keep_activations && env && tc_variant() == 3 && tc3_geometry(d.H, d.V).ok && sc.bchunk >= d.B;
+}
+// Row count of the kept forward, remembered per workspace so that the backward does not have to read it back again
+// (autograd may run the backward on another host thread: a mutex-protected table, not thread-local state).
+struct KeptRows {
+    std::mutex mu;
+    std::unordered_map<const void*, long long> rows;
+};
+inline KeptRows& kept_rows() { static KeptRows k; return k; }
+
+inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
+                               const float* W, const float* bias, const int* labels, const int* ylen,
+                               const int* xlen, float* lse, float* lpb, float* lpl, cudaStream_t s,
+                               unsigned* launches) {
+    const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
+    if (!g.ok) return tc_unsupported(d);
+    TcScratch sc = tc_scratch_layout(d, scratch);
+    convert_w_kernel<<<dim3((d.V + 31) / 32, (d.H + 31) / 32), 256, 0, s>>>(W, sc.Wt, sc.Wb, d.H, d.V);
+    JointTcParams p;
+    tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
+    p.b0 = 0; p.nb = d.B;
+    p.lse = lse; p.lpb = lpb; p.lpl = lpl;
+    *launches += 2;
+    if (!tc_keep(d, sc)) return tc_dispatch<0>(d, g, sc, p, s);
+    // forward that keeps its activations: rows of dl / gm / zb are laid out exactly as the backward GEMMs want them
+    const int ntiles = d.B * g.nTb * g.nUb;
+    long long rows = (long long)ntiles * 128;
+    if (d.allow_host_sync) {
+        rows = compact_tiles(g, sc, xlen, ylen, 0, ntiles, s);
+        if (rows < 0) return RNNT_STATUS_EXECUTION_FAILED;
+        p.slot = sc.slot;
+        *launches += 1;
+    }
+    {
+        std::lock_guard<std::mutex> lk(kept_rows().mu);
+        kept_rows().rows[scratch] = rows;
+    }
+    p.dl = sc.dl; p.gm = sc.gm; p.zb = sc.zb; p.zld = tc_zld(d.H);
+    CUtensorMap tm, tmp, tme;
+    const Tc2Geom g3 = tc3_geometry(d.H, d.V);
+    if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, TC2_NC, g3.ks) ||
+        !make_tmap_f32(&tmp, p.pred, (uint64_t)d.B * d.maxU, d.H, g.UU, 32, true) ||
+        !make_tmap_f32(&tme, p.enc, (uint64_t)d.B * d.maxT, d.H, g.TT, 64, false))
+        return RNNT_STATUS_EXECUTION_FAILED;
+    p.NC = TC2_NC; p.NCH = d.V / TC2_NC; p.stages = g3.stages; p.nbuf = g3.nbuf; p.swap = 0; p.ks = g3.ks;
+    p.dbg = tc_dbg();
+    return tc3_launch<2>(g3, tm, tmp, tme, p, s);
 }
 
 // Library-owned side stream for the fork/join inside the backward (created once per process).
@@ -765,30 +825,49 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         const int nb = (d.B - b0 < sc.bchunk) ? d.B - b0 : sc.bchunk;
         JointTcParams p;
         tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
-        p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb; p.zld = d.H + 8;
+        p.b0 = b0; p.nb = nb; p.coef = coef; p.dl = sc.dl; p.zb = sc.zb; p.zld = tc_zld(d.H);
         const int ntiles = nb * g.nTb * g.nUb;
         size_t rows = (size_t)ntiles * 128;
         const int* slot = nullptr;
-        if (compact) {
-            // Ragged batches: only tiles that intersect the valid lattice get rows in dl / zb / dZ, so the two GEMMs
-            // run over the valid rows instead of the padded ones.  Their row count must be known on the HOST: one
-            // 4-byte read-back + stream synchronise per chunk (before anything of this chunk is enqueued, so the
-            // GPU only idles for the launch latency).  Off by default in the C ABI (host_sync_ok == 0).
-            tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count);
-            int* hcount = host_count();
-            if (!hcount || cudaMemcpyAsync(hcount, sc.count, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-                cudaStreamSynchronize(s) != cudaSuccess)
-                return RNNT_STATUS_EXECUTION_FAILED;
-            rows = (size_t)(*hcount) * 128;
-            slot = sc.slot;
-            *launches += 1;
+        const bool keep = tc_keep(d, sc);
+        if (keep) {
+            // the forward kept numerators / maxima / tanh outputs in exactly these rows: one streaming pass turns them into dlogits
+            {
+                std::lock_guard<std::mutex> lk(kept_rows().mu);
+                auto it = kept_rows().rows.find(scratch);
+                if (it == kept_rows().rows.end()) {
+                    fprintf(stderr, "rnnt_b200: backward with keep_activations without a matching forward on this workspace\n");
+                    return RNNT_STATUS_INVALID_VALUE;
+                }
+                rows = (size_t)it->second;
+                kept_rows().rows.erase(it);
+            }
+            if (compact) slot = sc.slot;
             if (rows == 0) continue;
+            p.slot = slot; p.gm = sc.gm;
+            {
+                ScopedTimer tmr("dl_from_kept_kernel", s);
+                dl_from_kept_kernel<<<ntiles, 256, 0, s>>>(p);
+            }
+            *launches += 1;
+        } else {
+            if (compact) {
+                // Ragged batches: only tiles that intersect the valid lattice get rows in dl / zb / dZ, so the two GEMMs
+                // run over the valid rows instead of the padded ones (off by default in the C ABI: allow_host_sync == 0).
+                const long long r = compact_tiles(g, sc, xlen, ylen, b0, ntiles, s);
+                if (r < 0) return RNNT_STATUS_EXECUTION_FAILED;
+                rows = (size_t)r;
+                slot = sc.slot;
+                *launches += 1;
+                if (rows == 0) continue;
+            }
+            p.slot = slot;
+            rnntStatus_t st1 = tc_dispatch<1>(d, g, sc, p, s);
+            if (st1) return st1;
         }
-        p.slot = slot;
         const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU), slot};
-        rnntStatus_t st = tc_dispatch<1>(d, g, sc, p, s);
-        if (st) return st;
-        zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, d.H + 8);
+        rnntStatus_t st;
+        zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, tc_zld(d.H));
         // dZ[rows,H] (bf16) = dl[rows,V] . Wb[H,V]^T, then two independent branches:
         //   side stream : g = dZ*sech^2 -> d_enc, d_pred        (memory / MUFU bound)
         //   main stream : dWx[H+8,V] (+)= zb^T . dl  (row H = db) (tensor bound)

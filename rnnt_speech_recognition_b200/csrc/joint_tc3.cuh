@@ -11,6 +11,7 @@
 //
 // Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
 #pragma once
+#include <cuda_fp16.h>
 #include "joint_tc2.cuh"
 
 namespace rb {
@@ -24,10 +25,10 @@ inline Tc2Geom tc3_geometry(int H, int V) {
     // smem: enc/pred ring (2 x (2 x 16 KB pred boxes + 4 KB enc box)) + W ring; W stages shrink to fit
     const size_t in_bytes = (size_t)TC3_IN_STAGES * (2 * 16384 + 4096);
     const size_t bias_bytes = V <= 4096 ? (size_t)V * 4 : 0;
-    const size_t budget = 232448 - 1024 - 1024 - in_bytes - 16384 /*epilogue label-pick scratch*/ - bias_bytes;
+    const size_t budget = 232448 - 1024 - 1024 - in_bytes - bias_bytes;
     g.stages = (int)(budget / ((size_t)g.ks * 8192));
     if (g.stages > 6) g.stages = 6;
-    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024 + 16384 + bias_bytes;
+    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024 + bias_bytes;
     g.ok = g.stages >= 2;
     return g;
 }
@@ -55,8 +56,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     uint64_t* in_full = acc_empty + TC2_MAX_NBUF;         // [TC3_IN_STAGES]  input TMA -> producers
     uint64_t* in_empty = in_full + TC3_IN_STAGES;         // [TC3_IN_STAGES]  producers -> input TMA
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(in_empty + TC3_IN_STAGES);
-    uint8_t* ysm = reinterpret_cast<uint8_t*>(bars) + 1024;   // 128 threads x 32 floats: label-logit pick (MODE 0)
-    float* bias2 = reinterpret_cast<float*>(ysm + 16384);      // bias * log2(e) for V <= 4096 (else read from global)
+    float* bias2 = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 1024);   // bias * log2(e) for V <= 4096 (else read from global)
     const bool bias_in_smem = p.V <= 4096;
     if (bias_in_smem)
         for (int i = threadIdx.x; i < p.V; i += TC3_THREADS) bias2[i] = __ldg(p.bias + i) * 1.4426950408889634f;
@@ -196,10 +196,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             const TileInfo ti = decode_tile(p, tile);
             if (p.dbg & 8) continue;
             if (!ti.valid) {
-                if (MODE == 1 && !p.slot) {  // uncompacted rows: the plain GEMMs reduce over ALL rows, padding tiles must read as zero
+                if (MODE != 0 && !p.slot) {  // uncompacted rows: the plain GEMMs reduce over ALL rows, padding tiles must read as zero
                     const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                    uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
-                    for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
+                    if (MODE == 1) {         // (MODE 2: dl_from_kept_kernel zero-fills the dlogits rows of padding tiles)
+                        uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
+                        for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
+                    }
                     if (p.zb) {
                         const int h8 = p.H / 8;
                         for (int i = ptid; i < 128 * h8; i += 256)
@@ -231,10 +233,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
                 if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
-                if (MODE == 1 && p.zb) {
-                    uint4* zdst = reinterpret_cast<uint4*>(p.zb + (rowbase + r2) * p.zld + kb * 64 + hh * 32);
-                    zdst[0] = make_uint4(zr[0], zr[1], zr[2], zr[3]);   zdst[1] = make_uint4(zr[4], zr[5], zr[6], zr[7]);
-                    zdst[2] = make_uint4(zr[8], zr[9], zr[10], zr[11]); zdst[3] = make_uint4(zr[12], zr[13], zr[14], zr[15]);
+                if (MODE != 0 && p.zb) {
+                    __nv_bfloat16* zdst = p.zb + (rowbase + r2) * p.zld + kb * 64 + hh * 32;   // 64 bytes of this thread's row
+                    ptx::st_global_256(zdst, zr);
+                    ptx::st_global_256(zdst + 16, zr + 8);
                 }
                 if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);   // previous tile's MMAs have retired: z columns reusable
                 ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zr);
@@ -282,14 +284,29 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
-                    if (MODE == 0) {
+                    if (MODE != 1) {
                         float gm = y[0];
 #pragma unroll
                         for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
                         const float mn = fmaxf(m2, gm);
                         float acc = 0.f;
+                        if (MODE == 0) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) acc += ptx::ex2_approx(y[i] - mn);
+                            for (int i = 0; i < 32; ++i) acc += ptx::ex2_approx(y[i] - mn);
+                        } else {
+                            // keep the numerators: 2^(y - mn) in (0, 1] as fp16 (2^-11 relative), with mn beside them
+                            uint32_t o[16];
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                const float e0 = ptx::ex2_approx(y[i] - mn), e1 = ptx::ex2_approx(y[i + 1] - mn);
+                                acc += e0 + e1;
+                                o[i >> 1] = ptx::pack_f16x2(e0, e1);
+                            }
+                            __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
+                            ptx::st_global_256(dst, o);
+                            ptx::st_global_256(dst + 16, o + 8);
+                            p.gm[rowbase * (size_t)(p.V >> 5) + (size_t)(col0 >> 5) * 128 + r] = mn;   // [row block][group][row]: coalesced
+                        }
                         s = s * ptx::ex2_approx(m2 - mn) + acc;
                         m2 = mn;
                         if (p.blank >= col0 && p.blank < col0 + 32) {
@@ -298,29 +315,30 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                                 if (col0 + i == p.blank) yb = y[i];
                         }
                         // logit[label_u]: the label differs per thread, so the wanted element sits at a DYNAMIC index of
-                        // this thread's 32 registers.  Instead of 32 compare+select pairs, the group is parked in a
-                        // thread-private, XOR-swizzled (conflict-free) smem row and one element is read back -- only
-                        // when some lane of the warp has its label in this column group.
+                        // this thread's 32 registers: a binary select tree on the five index bits (31 selects, registers
+                        // only -- the load/store pipe is the scarce unit of this kernel), run only when some lane of the
+                        // warp has its label in this column group.
                         const int d = lab - col0;
                         const bool mine = (unsigned)d < 32u;
                         if (__any_sync(0xffffffffu, mine)) {
-                            uint8_t* yrow = ysm + (size_t)(warp * 32 + lane) * 128;
+                            float s16[16], s8[8], s4[4];
 #pragma unroll
-                            for (int cc = 0; cc < 8; ++cc)
-                                *reinterpret_cast<float4*>(yrow + ((cc ^ (lane & 7)) << 4)) =
-                                    make_float4(y[4 * cc], y[4 * cc + 1], y[4 * cc + 2], y[4 * cc + 3]);
-                            if (mine) yl = *reinterpret_cast<const float*>(yrow + ((((d >> 2) ^ (lane & 7)) << 4) + ((d & 3) << 2)));
+                            for (int i = 0; i < 16; ++i) s16[i] = (d & 1) ? y[2 * i + 1] : y[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) s8[i] = (d & 2) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) s4[i] = (d & 4) ? s8[2 * i + 1] : s8[2 * i];
+                            const float s2a = (d & 8) ? s4[1] : s4[0], s2b = (d & 8) ? s4[3] : s4[2];
+                            if (mine) yl = (d & 16) ? s2b : s2a;
                         }
                     } else {
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 32; i += 2)
                             o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
-                        uint4* dst = reinterpret_cast<uint4*>(p.dl + (rowbase + r) * p.V + col0);
-                        dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                        dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                        dst[2] = make_uint4(o[8], o[9], o[10], o[11]);
-                        dst[3] = make_uint4(o[12], o[13], o[14], o[15]);
+                        __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
+                        ptx::st_global_256(dst, o);
+                        ptx::st_global_256(dst + 16, o + 8);
                     }
                 }
                 ptx::tc_fence_before();
@@ -332,7 +350,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 drow[p.blank] = __float2bfloat16(csb);
                 if (lab >= 0) drow[lab] = __float2bfloat16(csl);
             }
-            if (MODE == 0 && rv) {
+            if (MODE != 1 && rv) {
                 const float lse2 = m2 + log2f(s);
                 p.lse[cell] = lse2 * LN2;
                 const long long k = sk_index(ti.b, t, u, p.maxU, p.SK);
@@ -344,6 +362,71 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     ptx::tc_fence_before();
     __syncthreads();
     if (warp == 13) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+}
+
+
+// Backward of a forward that kept its activations (MODE 2): dlogits[row, v] = e[row, v] * g * 2^(gm[row, v/32] + kd)
+// with e the kept fp16 numerators -- a pure streaming pass (2 bytes in, 2 bytes out per logit, IN PLACE: the bf16
+// result overwrites the fp16 input) instead of a second projection on the tensor cores.  The two special columns
+// (blank, label) receive their precomputed final values afterwards, from the thread that wrote that 16-byte vector.
+//   grid = tiles of the launch (original order), block = 256: warp <-> row (16 rows each), lane <-> 16-byte vectors.
+__device__ __forceinline__ void st_bf16_after(__nv_bfloat16* ptr, float val) {
+    // a 2-byte store that the compiler may not move across the surrounding (differently typed) vector accesses;
+    // same thread + same address, so the hardware keeps it after the 16-byte store it patches
+    asm volatile("st.global.b16 [%0], %1;" :: "l"(ptr), "h"(__bfloat16_as_ushort(__float2bfloat16(val))) : "memory");
+}
+__global__ void __launch_bounds__(256) dl_from_kept_kernel(const JointTcParams p) {
+    constexpr float LOG2E = 1.4426950408889634f;
+    const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nvec = p.V >> 3;
+    const TileInfo ti = decode_tile(p, tile);
+    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+    if (!ti.valid) {
+        if (!p.slot) {   // uncompacted rows: padding tiles must read as zero in the GEMMs
+            uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
+            for (int i = threadIdx.x; i < 128 * nvec; i += 256) d4[i] = z4;
+        }
+        return;
+    }
+    const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;
+    for (int r = warp; r < 128; r += 8) {
+        const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
+        const bool rv = t < ti.Tn && u < ti.Un;
+        uint4* row4 = reinterpret_cast<uint4*>(p.dl + (rowbase + r) * p.V);
+        if (!rv) {
+            for (int v = lane; v < nvec; v += 32) row4[v] = z4;
+            continue;
+        }
+        const float4 cf = p.coef[((long long)ti.b * p.maxT + t) * p.maxU + u];
+        const float kd2 = cf.x * LOG2E, cg = cf.y;
+        const int lab = (u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
+        const float* gmr = p.gm + rowbase * (size_t)(p.V >> 5) + r;   // [row block][group][row]
+        for (int v0 = lane; v0 < nvec; v0 += 128) {
+            uint4 x[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                     // four independent 16-byte requests per lane before any use
+                if (v0 + 32 * k < nvec) x[k] = row4[v0 + 32 * k];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = v0 + 32 * k;
+                if (v < nvec) {
+                    const float sc = cg * ptx::ex2_approx(gmr[(size_t)(v >> 2) * 128] + kd2);
+                    const uint32_t w[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float f0, f1;
+                        ptx::unpack_f16x2(w[i], f0, f1);
+                        o[i] = ptx::pack_bf16x2(f0 * sc, f1 * sc);
+                    }
+                    row4[v] = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+            }
+        }
+        // the two special columns, patched by the lane that wrote their vector (vector index & 31 == lane)
+        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(row4);
+        if (((p.blank >> 3) & 31) == lane) st_bf16_after(drow + p.blank, cf.z);   // (label == blank: cf.w == cf.z)
+        if (lab >= 0 && ((lab >> 3) & 31) == lane) st_bf16_after(drow + lab, cf.w);
+    }
 }
 
 template <int MODE>
@@ -358,7 +441,7 @@ inline rnntStatus_t tc3_launch(const Tc2Geom& g3, const CUtensorMap& tm, const C
     }
     const int ntiles = p.nb * p.nTb * p.nUb;
     const int grid = ntiles < tc_num_sms() ? ntiles : tc_num_sms();
-    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : "joint_tc3_kernel<dlogits>", s);
+    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : MODE == 1 ? "joint_tc3_kernel<dlogits>" : "joint_tc3_kernel<fwd+keep>", s);
     joint_tc3_kernel<MODE><<<grid, TC3_THREADS, g3.smem_bytes, s>>>(tm, tmp, tme, p);
     return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
 }

@@ -177,6 +177,20 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {  // lo -> 
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
     return r;
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {   // lo -> bits [0,16), hi -> [16,32)
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ void unpack_f16x2(uint32_t w, float& lo, float& hi) {
+    asm("{\n.reg .f16 l, h;\nmov.b32 {l, h}, %2;\ncvt.f32.f16 %0, l;\ncvt.f32.f16 %1, h;\n}" : "=f"(lo), "=f"(hi) : "r"(w));
+}
+// 32 bytes per lane in one request (sm_100: STG.256).  Stores whose lanes hit 32 different rows cost one LSU wavefront
+// per lane whatever their width, so doubling the width halves the wavefronts of such a scattered tile write.
+__device__ __forceinline__ void st_global_256(void* p, const uint32_t* v) {   // p 32-byte aligned, v[0..7]
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 :: "l"(p), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred;
     asm volatile("{\n.reg .pred p;\nelect.sync _|p, 0xffffffff;\nselp.u32 %0, 1, 0, p;\n}" : "=r"(pred));

@@ -27,13 +27,13 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _desc(B, T, U, H, V, blank, precision, compact=True):
+def _desc(B, T, U, H, V, blank, precision, compact=True, keep=False):
     # torch callers synchronise with the host every step anyway (loss read-back), so the torch surface lets the
     # backward compact ragged batches (one 4-byte read-back); capture-safe callers pass compact=False.
     sync_ok = 1 if (compact and os.environ.get("RNNTB200_COMPACT", "1") != "0"
                     and not torch.cuda.is_current_stream_capturing()) else 0
     return _lib.JointDesc(B, T, U, H, V, int(blank), _PREC[precision],
-                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, sync_ok)
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, sync_ok, 1 if keep else 0)
 
 
 def _workspace(desc, device):
@@ -67,7 +67,7 @@ def _check(enc, pred, W, b, labels, input_lengths, label_lengths):
 
 class _JointRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision, compact):
+    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision, compact, keep=None):
         L = _lib.load()
         enc, pred, W, b = (t.contiguous() for t in (enc, pred, W, b))
         labels, input_lengths, label_lengths = (t.contiguous() for t in (labels, input_lengths, label_lengths))
@@ -76,14 +76,16 @@ class _JointRNNT(torch.autograd.Function):
         U, V = pred.shape[1], W.shape[1]
         lab = labels if labels.numel() else torch.zeros(1, dtype=torch.int32, device=enc.device)
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, blank, precision, compact)
+            # a backward will follow: let the forward keep its softmax numerators / tanh outputs in the workspace
+            keep = any(ctx.needs_input_grad[:4]) if keep is None else bool(keep)
+            desc = _desc(B, T, U, H, V, blank, precision, compact, keep)
             ws = _workspace(desc, enc.device)
             costs = torch.empty(B, dtype=torch.float32, device=enc.device)
             st = L.rnntb200_joint_loss_forward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                _ptr(label_lengths), _ptr(input_lengths), _ptr(costs), _ptr(ws))
         _lib.check(st, "rnntb200_joint_loss_forward")
         ctx.save_for_backward(enc, pred, W, b, lab, input_lengths, label_lengths)
-        ctx.ws, ctx.dims, ctx.blank, ctx.precision, ctx.compact = ws, (B, T, U, H, V), blank, precision, compact
+        ctx.ws, ctx.dims, ctx.blank, ctx.precision, ctx.compact, ctx.keep = ws, (B, T, U, H, V), blank, precision, compact, keep
         return costs
 
     @staticmethod
@@ -94,23 +96,28 @@ class _JointRNNT(torch.autograd.Function):
         g = grad_costs.to(torch.float32).contiguous()
         d_enc, d_pred, dW, db = (torch.empty_like(t) for t in (enc, pred, W, b))
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.compact)
+            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.compact, ctx.keep)
             st = L.rnntb200_joint_loss_backward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                 _ptr(label_lengths), _ptr(input_lengths), _ptr(g), _ptr(d_enc),
                                                 _ptr(d_pred), _ptr(dW), _ptr(db), _ptr(ctx.ws))
         _lib.check(st, "rnntb200_joint_loss_backward")
         ctx.ws = None
-        return d_enc, d_pred, dW, db, None, None, None, None, None, None
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None
 
 
 def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank=0, precision="bf16",
-                    compact=True):
+                    compact=True, keep_activations=None):
     """Per-utterance RNN-T NLL (B,) of logits = tanh(enc_acts[:,:,None]+pred_acts[:,None]) @ W + b,
     differentiable w.r.t. enc_acts, pred_acts, W, b -- without ever materialising (B,T,U,V).
     precision: 'bf16' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (exact CUDA-core path).
     compact: let the bf16 backward skip padding tiles of ragged batches (one 4-byte host read-back per chunk);
-    pass False for a fully sync-free call (stream capture of the whole step is not validated yet, tools/graph_capture.py)."""
-    return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact)
+    pass False for a fully sync-free call (stream capture of the whole step is not validated yet, tools/graph_capture.py).
+    keep_activations: None = automatically when a gradient is required (the bf16 forward then leaves its softmax
+    numerators (fp16) and tanh outputs in the workspace and the backward is one streaming pass + two GEMMs);
+    False = the backward recomputes the projection on the tensor cores (2 bytes per logit less workspace traffic,
+    one more tensor-core pass)."""
+    return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact,
+                            keep_activations)
 
 
 def joint_logits(enc_acts, pred_acts, W, b):
