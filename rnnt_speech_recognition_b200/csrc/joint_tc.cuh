@@ -386,11 +386,6 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
 //   g = dZ * sech^2(enc+pred), with sech^2 evaluated from exp (relative accuracy near |z| -> 1,
 //   where 1 - tanh^2 computed from a rounded tanh would lose all its digits)
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float sech2(float x) {
-    const float e = ptx::ex2_approx(-2.8853900817779268f * fabsf(x));  // exp(-2|x|)
-    const float r = __frcp_rn(1.f + e);                                   // 1+e in [1,2]: one Newton-free reciprocal
-    return 4.f * e * r * r;
-}
 struct RowMap { int TT, UU, nTb, nUb, b0, lgUU; const int* slot; };   // TT*UU == 128, both powers of two
 __device__ __forceinline__ size_t tile_row(const RowMap& m, int b, int t, int u) {
     const int lgTT = 7 - m.lgUU;
@@ -475,15 +470,26 @@ __global__ void __launch_bounds__(128) denc_rows_kernel(__nv_bfloat16* __restric
     for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
     if (t < Tn) {
         const F8 e = load_f32x8(enc + ((size_t)b * maxT + t) * H + h);
+        const float* prow = pred + (size_t)b * maxU * H + h;
+        // rows of one u-block of the tile grid are contiguous: one tile_row() per block, pointer increments inside.
+        // sech^2 = 1 - tanh^2 with the same tanh.approx the forward used for z: one MUFU op and two FMAs per element
+        // (this kernel is issue-bound, not bandwidth-bound).
+        for (int u0 = 0; u0 < Un; u0 += m.UU) {
+            __nv_bfloat16* row = dz + tile_row(m, b, t, u0) * H + h;
+            const int un = min(m.UU, Un - u0);
 #pragma unroll 4
-        for (int u = 0; u < Un; ++u) {
-            __nv_bfloat16* row = dz + tile_row(m, b, t, u) * H + h;
-            const F8 d = load_bf16x8(row);
-            const F8 q = load_f32x8(pred + ((size_t)b * maxU + u) * H + h);
-            F8 g;
+            for (int ul = 0; ul < un; ++ul, row += H, prow += H) {
+                const F8 d = load_bf16x8(row);
+                const F8 q = load_f32x8(prow);
+                F8 g;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) { g.v[i] = d.v[i] * sech2(e.v[i] + q.v[i]); acc.v[i] += g.v[i]; }
-            store_bf16x8(row, g);
+                for (int i = 0; i < 8; ++i) {
+                    const float z = ptx::tanh_approx(e.v[i] + q.v[i]);
+                    g.v[i] = fmaf(-d.v[i] * z, z, d.v[i]);
+                    acc.v[i] += g.v[i];
+                }
+                store_bf16x8(row, g);
+            }
         }
     }
     store_f32x8(d_enc + ((size_t)b * maxT + t) * H + h, acc);
@@ -846,8 +852,15 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             if (rows == 0) continue;
             p.slot = slot; p.gm = sc.gm;
             {
+                const size_t gsm = (size_t)128 * (d.V / 32 + 1) * sizeof(float);   // the tile's maxima, transposed
+                static size_t gsm_set = 0;
+                if (gsm > 48 * 1024 && gsm > gsm_set) {
+                    if (cudaFuncSetAttribute(dl_from_kept_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm) != cudaSuccess)
+                        return RNNT_STATUS_EXECUTION_FAILED;
+                    gsm_set = gsm;
+                }
                 ScopedTimer tmr("dl_from_kept_kernel", s);
-                dl_from_kept_kernel<<<ntiles, 256, 0, s>>>(p);
+                dl_from_kept_kernel<<<ntiles, 256, gsm, s>>>(p);
             }
             *launches += 1;
         } else {
@@ -878,12 +891,14 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         cudaEventRecord(ss.fork, s);
         cudaStreamWaitEvent(ss.stream, ss.fork, 0);
         {
-            const int rthreads = ((d.H / 8 + 31) / 32) * 32;
-            ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", ss.stream);
-            denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, ss.stream>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
-            delete t1; t1 = new ScopedTimer("dpred_rows_kernel", ss.stream);
-            dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, ss.stream>>>(sc.dz, xlen, ylen, m, d.maxU, d.H, d_pred);
-            delete t1;
+            {
+                const int rthreads = ((d.H / 8 + 31) / 32) * 32;
+                ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", ss.stream);
+                denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, ss.stream>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
+                delete t1; t1 = new ScopedTimer("dpred_rows_kernel", ss.stream);
+                dpred_rows_kernel<<<dim3(d.maxU, nb), rthreads, 0, ss.stream>>>(sc.dz, xlen, ylen, m, d.maxU, d.H, d_pred);
+                delete t1;
+            }
         }
         cudaEventRecord(ss.join, ss.stream);
         st = bwd_gemm_dw(d, sc, rows, /*accumulate=*/b0 > 0, s, launches);

@@ -388,6 +388,15 @@ __global__ void __launch_bounds__(256) dl_from_kept_kernel(const JointTcParams p
         return;
     }
     const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;
+    // the tile's maxima [group][row] (coalesced in global) are staged as [row][group] (+1 word of padding per row:
+    // conflict-free both ways) so that a row's lanes read consecutive words
+    extern __shared__ float gm_s[];
+    const int G = p.V >> 5;
+    {
+        const float* gsrc = p.gm + rowbase * (size_t)G;
+        for (int i = threadIdx.x; i < G * 128; i += 256) gm_s[(i & 127) * (G + 1) + (i >> 7)] = gsrc[i];
+    }
+    __syncthreads();
     for (int r = warp; r < 128; r += 8) {
         const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
         const bool rv = t < ti.Tn && u < ti.Un;
@@ -399,7 +408,7 @@ __global__ void __launch_bounds__(256) dl_from_kept_kernel(const JointTcParams p
         const float4 cf = p.coef[((long long)ti.b * p.maxT + t) * p.maxU + u];
         const float kd2 = cf.x * LOG2E, cg = cf.y;
         const int lab = (u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
-        const float* gmr = p.gm + rowbase * (size_t)(p.V >> 5) + r;   // [row block][group][row]
+        const float* gmr = gm_s + r * (G + 1);
         for (int v0 = lane; v0 < nvec; v0 += 128) {
             uint4 x[4];
 #pragma unroll
@@ -409,7 +418,7 @@ __global__ void __launch_bounds__(256) dl_from_kept_kernel(const JointTcParams p
             for (int k = 0; k < 4; ++k) {
                 const int v = v0 + 32 * k;
                 if (v < nvec) {
-                    const float sc = cg * ptx::ex2_approx(gmr[(size_t)(v >> 2) * 128] + kd2);
+                    const float sc = cg * ptx::ex2_approx(gmr[v >> 2] + kd2);
                     const uint32_t w[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
                     uint32_t o[4];
 #pragma unroll
