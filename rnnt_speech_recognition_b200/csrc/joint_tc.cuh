@@ -56,10 +56,21 @@ inline TcGeom tc_geometry(int maxT, int maxU, int H, int V) {
     TcGeom g{};
     g.ok = false;
     if (H % 64 || V % 64 || H > 64 * TC_MAX_KB) return g;
-    int best = 128, best_pad = 1 << 30;
-    for (int uu = 128; uu >= 8; uu >>= 1) {  // least padding along U, ties -> widest
-        const int pad = (maxU + uu - 1) / uu * uu;
-        if (pad < best_pad) { best_pad = pad; best = uu; }
+    // tile shape: least padded lattice cells first; among equals the shape that loads the fewest enc + pred rows per
+    // tile (TT + UU): every tile re-reads its TT enc rows and UU pred rows (fp32, H wide) from L2, and the L2 -> SM
+    // stream is what bounds the fused kernel (1 x 128 tiles: 330 KB per tile; 8 x 16: 61 KB).  TT <= 16 (enc TMA box).
+    int best = 128;
+    long long best_pad = 1ll << 60;
+    int best_rows = 1 << 30;
+    for (int uu = 128; uu >= 8; uu >>= 1) {
+        const int tt = 128 / uu;
+        const long long pad = (long long)((maxU + uu - 1) / uu * uu) * ((maxT + tt - 1) / tt * tt);
+        if (pad < best_pad || (pad == best_pad && tt + uu < best_rows)) { best_pad = pad; best_rows = tt + uu; best = uu; }
+    }
+    {   // RNNTB200_TILE_UU = 8..128 forces the tile width (A/B measurements)
+        static int force = -1;
+        if (force < 0) { const char* e = getenv("RNNTB200_TILE_UU"); force = e ? atoi(e) : 0; }
+        if (force >= 8 && force <= 128 && (force & (force - 1)) == 0) best = force;
     }
     g.UU = best;
     g.TT = 128 / best;
