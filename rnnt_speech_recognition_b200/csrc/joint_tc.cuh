@@ -65,7 +65,8 @@ inline TcGeom tc_geometry(int maxT, int maxU, int H, int V) {
     for (int uu = 128; uu >= 8; uu >>= 1) {
         const int tt = 128 / uu;
         const long long pad = (long long)((maxU + uu - 1) / uu * uu) * ((maxT + tt - 1) / tt * tt);
-        if (pad < best_pad || (pad == best_pad && tt + uu < best_rows)) { best_pad = pad; best_rows = tt + uu; best = uu; }
+        // (ties -> the narrower tile: 16 x 8 is the shape the single-pass reduction is written for)
+        if (pad < best_pad || (pad == best_pad && tt + uu <= best_rows)) { best_pad = pad; best_rows = tt + uu; best = uu; }
     }
     {   // RNNTB200_TILE_UU = 8..128 forces the tile width (A/B measurements)
         static int force = -1;
@@ -525,6 +526,116 @@ __global__ void __launch_bounds__(128) dpred_rows_kernel(const __nv_bfloat16* __
     }
     store_f32x8(d_pred + ((size_t)b * maxU + u) * H + h, acc);
 }
+// Single-pass reduction for 16 x 8 tiles: g = dZ * (1 - tanh^2) is formed once, in registers, and never written back.
+// A block owns one u-block column (8 label positions) of one utterance and sweeps a segment of its tiles along t, so
+// it reads WHOLE tiles (128 contiguous rows) one after the other; thread <-> EIGHT columns of H (16-byte loads: the
+// number of outstanding load requests per SM is what limits a streaming kernel, so each request should carry 512
+// bytes per warp -- the same design with 4-byte loads ran at 1 TB/s).  Per time step the 8 rows are summed over u
+// straight into a partial plane of d_enc (one plane per u-block); the 8 column sums over t accumulate in registers
+// across the sweep and go to a partial plane of d_pred (one per segment); sum_planes_kernel adds the planes.
+// HBM traffic: one read of the bf16 dZ plus the small fp32 planes, instead of read + write-back + second read.
+constexpr int RED_THREADS = 96;                    // H <= 640 on the tensor-core path: 80 threads x 8 columns
+constexpr int RED_MIN_BLOCKS = 2368;               // ~4 waves of 4 blocks per SM
+constexpr int RED_UU = 8, RED_TT = 16;
+__global__ void __launch_bounds__(RED_THREADS, 4) dencpred_tiles_kernel(
+    const __nv_bfloat16* __restrict__ dz, const float* __restrict__ enc, const float* __restrict__ pred,
+    const int* __restrict__ xlen, const int* __restrict__ ylen, RowMap m, int maxT, int maxU, int H, int tiles_per_seg,
+    float* __restrict__ penc, float* __restrict__ ppred) {
+    __shared__ float4 q_s[RED_UU * 2 * RED_THREADS];   // the block's pred rows, [k][half][thread]: thread-private columns
+    const int ub = blockIdx.x, seg = blockIdx.y, bl = blockIdx.z, nb = gridDim.z, b = m.b0 + bl;
+    const int h = threadIdx.x * 8, u0 = ub * RED_UU;
+    if (h >= H) return;                             // (no block-wide barrier below)
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    float4* qs = q_s + threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < RED_UU; ++k) {
+        const float* src = pred + ((size_t)b * maxU + min(u0 + k, maxU - 1)) * H + h;   // (rows with u >= U_b carry dZ == 0)
+        qs[(2 * k) * RED_THREADS] = *reinterpret_cast<const float4*>(src);
+        qs[(2 * k + 1) * RED_THREADS] = *reinterpret_cast<const float4*>(src + 4);
+    }
+    float accP[RED_UU][8];
+#pragma unroll
+    for (int k = 0; k < RED_UU; ++k)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) accP[k][i] = 0.f;
+    const bool ub_valid = u0 < Un;
+    const int tb_end = min((seg + 1) * tiles_per_seg, m.nTb);
+    for (int tb = seg * tiles_per_seg; tb < tb_end; ++tb) {
+        const int t0 = tb * RED_TT;
+        float* pe = penc + (((size_t)ub * nb + bl) * maxT + t0) * H + h;
+        if (!(ub_valid && t0 < Tn)) {               // tile outside the valid lattice: its d_enc share is zero
+            for (int j = 0; j < RED_TT; ++j)
+                if (t0 + j < maxT) {
+                    *reinterpret_cast<float4*>(pe + (size_t)j * H) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(pe + (size_t)j * H + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            continue;
+        }
+        size_t q = ((size_t)bl * m.nTb + tb) * m.nUb + ub;
+        if (m.slot) q = (size_t)m.slot[q];
+        const __nv_bfloat16* base = dz + q * 128 * H + h;
+#pragma unroll 2
+        for (int j = 0; j < RED_TT; ++j) {
+            uint4 d[RED_UU];
+#pragma unroll
+            for (int k = 0; k < RED_UU; ++k)        // the 8 rows of this time step: 8 independent 16-byte requests
+                d[k] = *reinterpret_cast<const uint4*>(base + (size_t)(j * RED_UU + k) * H);
+            const int t = min(t0 + j, maxT - 1);    // (rows with t >= T_b carry dZ == 0)
+            const float* ep = enc + ((size_t)b * maxT + t) * H + h;
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(ep)), e1 = __ldg(reinterpret_cast<const float4*>(ep + 4));
+            const float e[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            float aE[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) aE[i] = 0.f;
+#pragma unroll
+            for (int k = 0; k < RED_UU; ++k) {
+                const float4 q0 = qs[(2 * k) * RED_THREADS], q1 = qs[(2 * k + 1) * RED_THREADS];
+                const float qv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+                const uint32_t w[4] = {d[k].x, d[k].y, d[k].z, d[k].w};
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float dv = (i & 1) ? __uint_as_float(w[i >> 1] & 0xffff0000u) : __uint_as_float(w[i >> 1] << 16);
+                    const float z = ptx::tanh_approx(e[i] + qv[i]);
+                    const float g = fmaf(-dv * z, z, dv);
+                    aE[i] += g;
+                    accP[k][i] += g;
+                }
+            }
+            if (t0 + j < maxT) {
+                *reinterpret_cast<float4*>(pe + (size_t)j * H) = make_float4(aE[0], aE[1], aE[2], aE[3]);
+                *reinterpret_cast<float4*>(pe + (size_t)j * H + 4) = make_float4(aE[4], aE[5], aE[6], aE[7]);
+            }
+        }
+    }
+    float* pp = ppred + (((size_t)seg * nb + bl) * maxU + u0) * H + h;
+#pragma unroll
+    for (int k = 0; k < RED_UU; ++k)
+        if (u0 + k < maxU) {
+            *reinterpret_cast<float4*>(pp + (size_t)k * H) = make_float4(accP[k][0], accP[k][1], accP[k][2], accP[k][3]);
+            *reinterpret_cast<float4*>(pp + (size_t)k * H + 4) = make_float4(accP[k][4], accP[k][5], accP[k][6], accP[k][7]);
+        }
+}
+// out[i] = sum_k part[k][i] over `nplanes` planes of `n4` float4 each
+__global__ void __launch_bounds__(256) sum_planes_kernel(const float4* __restrict__ part, int nplanes, size_t n4,
+                                                         float4* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int k = 0; k < nplanes; ++k) {
+            const float4 v = part[(size_t)k * n4 + i];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        out[i] = acc;
+    }
+}
+// segments of the t sweep: enough blocks to fill the GPU a few times over (pure function of the geometry)
+inline int red_tiles_per_seg(int nTb, int nUb, int nb) {
+    long long blocks = (long long)nUb * nb;
+    int nseg = (int)((RED_MIN_BLOCKS + blocks - 1) / blocks);
+    if (nseg < 1) nseg = 1;
+    if (nseg > nTb) nseg = nTb;
+    return (nTb + nseg - 1) / nseg;
+}
 // zb[row, H .. H+7] = (1, 0, ..., 0): the ones column that turns the dW GEMM's extra output row into db
 __global__ void __launch_bounds__(256) zb_ones_kernel(__nv_bfloat16* __restrict__ zb, size_t rows, int H, int zld) {
     const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -593,6 +704,7 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 struct TcScratch {
     __nv_bfloat16 *Wt, *Wb, *dl, *zb, *dz;   // zb rows have stride tc_zld(H) (ones column at H); dz is bf16
     float* dWx;                             // (H+8, V) fp32: dW rows, then the db row produced by the ones column
+    float *penc, *ppred;                    // partial planes of the single-pass reduction: (nUb, bchunk, maxT, H) and (nSeg, bchunk, maxU, H)
     float* gm;                              // (row blocks, V/32, 128) fp32: running maxima of the kept numerators (keep_activations)
     int* slot;                              // tile -> compact row block (per backward chunk)
     int* count;                             // number of valid tiles of the chunk
@@ -618,6 +730,11 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.dl = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.V * 2));
     s.zb = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * tc_zld(d.H) * 2));
     s.dz = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.H * 2));
+    {
+        const int tps = red_tiles_per_seg(g.nTb, g.nUb, (int)bc), nseg = (g.nTb + tps - 1) / tps;
+        s.penc = reinterpret_cast<float*>(take((size_t)g.nUb * bc * d.maxT * d.H * 4));
+        s.ppred = reinterpret_cast<float*>(take((size_t)nseg * bc * d.maxU * d.H * 4));
+    }
     s.gm = reinterpret_cast<float*>(take(s.rows_chunk * (size_t)(d.V / 32) * 4));
     s.dWx = reinterpret_cast<float*>(take((size_t)(d.H + 8) * d.V * 4));
     s.slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
@@ -830,6 +947,13 @@ inline SideStream& side_stream() {
     return ss;
 }
 
+// reduction phase: 0 = two streaming passes (g written back), 1 = single pass over whole tiles (RNNTB200_RED)
+inline int red_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_RED"); v = e ? atoi(e) : 1; }
+    return v;
+}
+
 inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                 const float* W, const float* bias, const int* labels, const int* ylen,
                                 const int* xlen, const float* lse, const float4* coef, float* d_enc, float* d_pred,
@@ -902,7 +1026,21 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         cudaEventRecord(ss.fork, s);
         cudaStreamWaitEvent(ss.stream, ss.fork, 0);
         {
-            {
+            if (red_variant() == 1 && g.UU == RED_UU && d.H <= 8 * RED_THREADS && d.H % 8 == 0) {
+                // nb (not bchunk) utterances in this launch: the planes are laid out for nb
+                const int tps = red_tiles_per_seg(g.nTb, g.nUb, nb), nseg = (g.nTb + tps - 1) / tps;
+                const dim3 grid(g.nUb, nseg, nb);
+                ScopedTimer* t1 = new ScopedTimer("dencpred_tiles_kernel", ss.stream);
+                dencpred_tiles_kernel<<<grid, RED_THREADS, 0, ss.stream>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, tps,
+                                                                       sc.penc, sc.ppred);
+                delete t1; t1 = new ScopedTimer("sum_planes_kernel", ss.stream);
+                const size_t ne4 = (size_t)nb * d.maxT * d.H / 4, np4 = (size_t)nb * d.maxU * d.H / 4;
+                sum_planes_kernel<<<(unsigned)((ne4 + 255) / 256 < 4096 ? (ne4 + 255) / 256 : 4096), 256, 0, ss.stream>>>(
+                    reinterpret_cast<const float4*>(sc.penc), g.nUb, ne4, reinterpret_cast<float4*>(d_enc + (size_t)b0 * d.maxT * d.H));
+                sum_planes_kernel<<<(unsigned)((np4 + 255) / 256 < 4096 ? (np4 + 255) / 256 : 4096), 256, 0, ss.stream>>>(
+                    reinterpret_cast<const float4*>(sc.ppred), nseg, np4, reinterpret_cast<float4*>(d_pred + (size_t)b0 * d.maxU * d.H));
+                delete t1;
+            } else {
                 const int rthreads = ((d.H / 8 + 31) / 32) * 32;
                 ScopedTimer* t1 = new ScopedTimer("denc_rows_kernel", ss.stream);
                 denc_rows_kernel<<<dim3(d.maxT, nb), rthreads, 0, ss.stream>>>(sc.dz, enc, pred, xlen, ylen, m, d.maxT, d.maxU, d.H, d_enc);
