@@ -1,0 +1,40 @@
+"""Summarise an ncu report (`ncu --set full -o X`) into a small JSON: per kernel the duration, DRAM / L2 traffic, pipe
+utilisation and occupancy figures quoted in DESIGN.md.  `python tools/ncu_summary.py X.ncu-rep > summary.json`"""
+import csv
+import io
+import json
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "sm__cycles_elapsed.avg", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "lts__t_sector_hit_rate.pct", "l1tex__m_xbar2l1tex_read_sectors_mem_global_op_tma_ld.sum",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "launch__registers_per_thread",
+        "launch__grid_size", "launch__block_size"]
+
+
+def main(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    res = {}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        d = {}
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                d[w] = (r[i] + " " + units[i]).strip()
+        key, n = name, 2
+        while key in res:
+            key = "%s #%d" % (name, n)
+            n += 1
+        res[key] = d
+    print(json.dumps(res, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
