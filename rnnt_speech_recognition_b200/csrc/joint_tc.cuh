@@ -1015,7 +1015,9 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         }
         const RowMap m{g.TT, g.UU, g.nTb, g.nUb, b0, ilog2(g.UU), slot};
         rnntStatus_t st;
-        zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, tc_zld(d.H));
+        // (the generation-3 kernel writes the ones column of zb itself)
+        if (!(tc_variant() == 3 && tc3_geometry(d.H, d.V).ok))
+            zb_ones_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(sc.zb, rows, d.H, tc_zld(d.H));
         // dZ[rows,H] (bf16) = dl[rows,V] . Wb[H,V]^T, then two independent branches:
         //   side stream : g = dZ*sech^2 -> d_enc, d_pred        (memory / MUFU bound)
         //   main stream : dWx[H+8,V] (+)= zb^T . dl  (row H = db) (tensor bound)

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                         for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
                     }
                     if (p.zb) {
-                        const int h8 = p.H / 8;
+                        const int h8 = p.H / 8 + 1;   // + the 8 columns at H (ones column): the dW GEMM reads H + 8 columns
                         for (int i = ptid; i < 128 * h8; i += 256)
                             *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + i / h8) * p.zld + (i % h8) * 8) = z4;
                     }
@@ -237,6 +237,10 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                     __nv_bfloat16* zdst = p.zb + (rowbase + r2) * p.zld + kb * 64 + hh * 32;   // 64 bytes of this thread's row
                     ptx::st_global_256(zdst, zr);
                     ptx::st_global_256(zdst + 16, zr + 8);
+                    // the ones column at index H that turns the dW GEMM's extra output row into db (written once per row,
+                    // by the thread that owns the row's last 32 columns)
+                    if (kb == KB - 1 && hh == 1)
+                        *reinterpret_cast<uint4*>(p.zb + (rowbase + r2) * p.zld + p.H) = make_uint4(0x00003F80u, 0u, 0u, 0u);
                 }
                 if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);   // previous tile's MMAs have retired: z columns reusable
                 ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zr);
