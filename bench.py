@@ -232,6 +232,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|WARN|INFO) go to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     gB = B * world
