@@ -231,9 +231,13 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # stdout carries ONE JSON line.  NCCL prints its version banner (NCCL_DEBUG=VERSION on the GPU boxes) with a plain
+    # printf, so file descriptor 1 is pointed at stderr for the whole run and the result line is written to the saved
+    # descriptor at the end.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own banner / debug lines (NCCL_DEBUG=VERSION|WARN|INFO) go to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     gB = B * world
@@ -360,7 +364,8 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_budget)
-        print(json.dumps(out))
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
