@@ -6,10 +6,12 @@ Public names follow the reference:
   rnnt_loss              warprnnt_tensorflow/__init__.py:9   (per-utterance costs)
   torch_rnnt_loss, RNNTLoss, certify_inputs   warprnnt_pytorch/__init__.py:53-140
   Joint, joint_rnnt_loss model.py:158-166 fused with the loss (no (B,T,U,V) tensor)
+  joint_train_step       run_rnnt.py:259-296 for the joint (loss/B scaling, one packed all-reduce, SGD step)
 """
 from .loss import encoder_lengths, get_loss_fn
 from .warprnnt import RNNTLoss, certify_inputs, rnnt_loss, torch_rnnt_loss
 from .joint import Joint, get_fused_loss_fn, joint_logits, joint_rnnt_loss
+from .train import joint_train_step, make_optimizer
 
 __all__ = ["get_loss_fn", "encoder_lengths", "rnnt_loss", "torch_rnnt_loss", "RNNTLoss", "certify_inputs", "Joint",
-           "joint_rnnt_loss", "joint_logits", "get_fused_loss_fn"]
+           "joint_rnnt_loss", "joint_logits", "get_fused_loss_fn", "joint_train_step", "make_optimizer"]

@@ -50,3 +50,19 @@ def allreduce_loss_and_weight_grads(loss_sum, dW, db, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
     return unpack(buf, dW.shape, db.shape)
+
+
+def allreduce_packed_(tensors, group=None):
+    """In-place SUM over ranks of a list of fp32 tensors with ONE collective (flatten -> all_reduce -> copy back).
+    The general form of allreduce_loss_and_weight_grads for callers whose joint has more parameters than (W, b)
+    (the un-hoisted Dense-1 of model.py:162-163).  A no-op when torch.distributed is not initialised or world == 1."""
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return tensors
+    flat = torch.cat([t.reshape(-1).to(torch.float32) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    off = 0
+    for t in tensors:
+        n = t.numel()
+        t.copy_(flat[off:off + n].view_as(t))
+        off += n
+    return tensors

@@ -100,3 +100,27 @@ def test_joint_module_forward_and_decode_step():
     ref = rb.rnnt_loss(torch.tanh((f[:, :, None] + g[:, None]) @ j.kernel_1 + j.bias_1) @ j.kernel_2 + j.bias_2, lab, il, ll)
     assert torch.allclose(costs, ref, rtol=1e-5, atol=1e-4)
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in j.parameters())
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_train_step_runs_and_learns(precision):
+    """run_rnnt.py:259-296 for the joint -- loss / global batch, backward, (packed all-reduce: world 1
+    here, world 2 in tests/test_dist_gloo.py), SGD-momentum step.  A few steps on a fixed batch must lower the loss,
+    and the encoder / prediction inputs must receive gradients for the caller's networks."""
+    import rnnt_speech_recognition_b200 as rb
+    torch.manual_seed(3)
+    B, T, U, P, H, V = 3, 14, 5, 64, 64, 64
+    joint = rb.Joint(P, H, V, precision=precision).cuda()
+    opt = rb.make_optimizer(joint.parameters(), learning_rate=0.02)
+    enc = torch.randn(B, T, P, device="cuda", requires_grad=True)
+    pred = torch.randn(B, U, P, device="cuda", requires_grad=True)
+    labels = torch.randint(1, V, (B, U - 1), device="cuda", dtype=torch.int32)
+    spec_lengths = torch.tensor([2 * T, 2 * T - 3, 2 * T - 1], device="cuda", dtype=torch.int32)   # ceil(./2) -> T, T-1, T
+    label_lengths = torch.tensor([U - 1, U - 2, U - 1], device="cuda", dtype=torch.int32)
+    losses = [rb.joint_train_step(joint, opt, enc, pred, labels, spec_lengths, label_lengths, global_batch_size=B).item()
+              for _ in range(6)]
+    assert all(np.isfinite(losses)), losses
+    assert losses[-1] < losses[0], losses
+    assert enc.grad is not None and torch.isfinite(enc.grad).all() and enc.grad.abs().sum() > 0
+    assert pred.grad is not None and torch.isfinite(pred.grad).all()
+    assert not enc.grad[1, T - 1:].any()          # frames past ceil(spec_length / 2) receive no gradient
