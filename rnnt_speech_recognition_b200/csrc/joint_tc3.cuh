@@ -10,6 +10,12 @@
 // pass, no inter-warp barrier, no register prefetch buffers.
 //
 // Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
+//
+// MODE 0  forward: lse + (blank, label) log-probs per cell; nothing else leaves the SM
+// MODE 1  recompute backward: same mainloop, epilogue writes the bf16 logit gradients, producers the bf16 z rows
+// MODE 2  forward that KEEPS its activations (rnntb200JointDesc.keep_activations): MODE 0 + the fp16 softmax
+//         numerators 2^(y - m) the epilogue computes anyway, the running maxima m, and the bf16 z rows;
+//         dl_from_kept_kernel (below) then turns the numerators into logit gradients in one streaming pass.
 #pragma once
 #include <cuda_fp16.h>
 #include "joint_tc2.cuh"
