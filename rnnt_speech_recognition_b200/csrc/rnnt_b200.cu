@@ -14,7 +14,6 @@
 #ifndef RNNTB200_NO_TC
 #include "joint_tc.cuh"
 #include "mma_probe.cuh"
-#include "mma2_probe.cuh"
 #endif
 
 namespace {
@@ -435,11 +434,6 @@ rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* e
 
 #ifndef RNNTB200_NO_TC
 // bring-up probe (not part of the public header): cycles per tcgen05.mma, see csrc/mma_probe.cuh
-// bring-up probe of the 2-CTA MMA form (csrc/mma2_probe.cuh; tools/mma2_probe.py): mode 0 dumps accumulators, mode 1 times
-int rnntb200_debug_mma2_probe(int mode, int iters, int clusters, float* out_dev) {
-    rb::mma2_probe_kernel<<<2 * clusters, 128, rb::c2::PROBE_KB * 4096 + 1024>>>(mode, iters, out_dev);
-    return (int)cudaDeviceSynchronize();
-}
 int rnntb200_debug_mma_probe(int variant, int iters, int ctas, float* out_dev) {
     cudaFuncSetAttribute(rb::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
     rb::mma_probe_kernel<<<ctas, 128, 100 * 1024>>>(variant, iters, out_dev);

@@ -13,7 +13,7 @@
 //     mapa); w_empty / acc_full / z_free are signalled in both CTAs by tcgen05.commit...multicast::cluster
 #pragma once
 #include "../joint_tc3.cuh"
-#include "../mma2_probe.cuh"
+#include "mma2_probe.cuh"
 
 namespace rb {
 namespace c2 {

@@ -8,9 +8,10 @@
 //   mode 1  cycles per cta_group::2 MMA when one elected lane of the LEADER issues 20 per block (the fused kernel's
 //           issue pattern), A walking over 320 columns, B over 5 K-block slabs
 // Status: compiles for sm_100a; NOT yet run on hardware (written after the round's GPU budget was spent).
-// Never called by the library; exported as rnntb200_debug_mma2_probe for the tool only.
+// Outside the library build: tools/build_wip.sh compiles it into csrc/wip/libwip.so (export rnntb200_wip_mma2_probe)
+// for tools/mma2_probe.py.
 #pragma once
-#include "ptx.cuh"
+#include "../ptx.cuh"
 
 namespace rb {
 namespace c2 {

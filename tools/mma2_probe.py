@@ -1,4 +1,4 @@
-"""Bring-up probe of the 2-CTA MMA form (csrc/mma2_probe.cuh): `timeout 60 python tools/mma2_probe.py`.
+"""Bring-up probe of the 2-CTA MMA form (csrc/wip/mma2_probe.cuh, built by tools/build_wip.sh into csrc/wip/libwip.so): `timeout 60 python tools/mma2_probe.py`.
 
 mode 0: every CTA of every pair dumps its 128 x 64 accumulator of D = A_cta . B^T with small-integer operands generated
         in the kernel; compared EXACTLY with the integer GEMM below.  A mismatch pattern tells which assumption of the
@@ -13,10 +13,12 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from rnnt_speech_recognition_b200 import _lib
-
-L = _lib.load()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SO = os.path.join(ROOT, "rnnt_speech_recognition_b200", "csrc", "wip", "libwip.so")
+if not os.path.exists(SO):
+    import subprocess
+    subprocess.run([os.path.join(ROOT, "tools", "build_wip.sh")], check=True)
+L = C.CDLL(SO)
 KB, N = 5, 64
 K = KB * 64
 
@@ -35,7 +37,7 @@ want = np.stack([probe_a(c, r, k).astype(np.float64) @ Bm.T for c in (0, 1)])   
 
 for clusters in (1, 74):
     out = torch.full((clusters, 2, 128, N), float("nan"), device="cuda")
-    rc = L.rnntb200_debug_mma2_probe(0, 0, clusters, C.c_void_p(out.data_ptr()))
+    rc = L.rnntb200_wip_mma2_probe(0, 0, clusters, C.c_void_p(out.data_ptr()))
     got = out.cpu().numpy().astype(np.float64)
     bad = int((got != want[None]).sum())
     print("mode 0  clusters %3d  rc %d  mismatching accumulator entries: %d of %d" % (clusters, rc, bad, got.size))
@@ -48,6 +50,6 @@ for clusters in (1, 74):
 
 t = torch.zeros(74, device="cuda")
 for clusters in (1, 74):
-    rc = L.rnntb200_debug_mma2_probe(1, 4000, clusters, C.c_void_p(t.data_ptr()))
+    rc = L.rnntb200_wip_mma2_probe(1, 4000, clusters, C.c_void_p(t.data_ptr()))
     o = t[:clusters].cpu()
     print("mode 1  clusters %3d  rc %d  cycles per 2-CTA MMA mean %.1f max %.1f (floor 32)" % (clusters, rc, o.mean().item(), o.max().item()))
