@@ -173,7 +173,8 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
 rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* enc, const float* pred,
                                    const float* W, const float* bias, float* logits, void* workspace);
 
-/** Number of kernels launched by this library in this process since load (bench.py's gpu_launches). */
+/** Number of kernels OF THIS LIBRARY launched in this process since load (bench.py's gpu_launches); the cuBLAS
+ *  GEMM calls of the bf16 backward are not included. */
 unsigned long long rnntb200_launch_count();
 
 /** Per-kernel CUDA-event instrumentation for bench.py's attribution pass.  set_timing(1) clears the record
