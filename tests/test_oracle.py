@@ -132,3 +132,32 @@ def test_invalid_arguments(oracle):
     assert oracle.get_workspace_size(0, 3, 2, False)[0] == 2    # rnnt_entrypoint.cpp:102-105
     assert oracle.get_workspace_size(4, 3, 2, False) == (0, 2 * 4 * 4 * 3 * 4)
     assert oracle.get_workspace_size(4, 3, 2, True) == (0, 2 * (3 * 4 * 3 + 2) * 4)
+
+
+def test_against_live_reference_property(oracle):
+    """Property-based pin (hypothesis, fixed seed database off): on random shapes, ragged lengths, blank positions and
+    logit scales the restatement and the unmodified reference library agree on costs and log-prob gradients."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libwarprnnt.so not available")
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, derandomize=True, database=None,
+              suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+    @given(st.integers(1, 4), st.integers(1, 12), st.integers(1, 7), st.integers(2, 11), st.integers(0, 2 ** 31 - 1),
+           st.sampled_from([0.3, 1.0, 6.0]))
+    def run(B, T, U, V, seed, scale):
+        rng = np.random.default_rng(seed)
+        acts = (scale * rng.standard_normal((B, T, U, V))).astype(np.float32)
+        blank = int(rng.integers(0, V))
+        cand = np.array([v for v in range(V) if v != blank])
+        labels = (rng.choice(cand, size=(B, U - 1)).astype(np.int32) if U > 1 else np.zeros((B, 0), np.int32))
+        il = rng.integers(1, T + 1, B).astype(np.int32)
+        ll = rng.integers(0, U, B).astype(np.int32)
+        il[0], ll[0] = T, U - 1                       # the reference sizes its slabs by maxT / maxU
+        lp = oracle.log_softmax(acts)
+        c, g = oracle.rnnt_cost_and_grad(lp, labels, il, ll, blank=blank)
+        cr, gr = oracle.ref_cpu_cost_and_grad(lp, labels, il, ll, blank=blank, num_threads=1)
+        assert np.allclose(c, cr, rtol=1e-5, atol=1e-6), (B, T, U, V, seed)
+        assert np.allclose(g, gr, rtol=1e-4, atol=1e-6), (B, T, U, V, seed)
+
+    run()
