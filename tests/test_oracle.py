@@ -161,3 +161,26 @@ def test_against_live_reference_property(oracle):
         assert np.allclose(g, gr, rtol=1e-4, atol=1e-6), (B, T, U, V, seed)
 
     run()
+
+
+def test_joint_oracle_against_torch_fp64_chain_property(oracle):
+    """The joint is parity-unpinned by the reference (TensorFlow arithmetic): its anchor is model.py:158-166 restated in
+    torch fp64 and chained by autograd through log_softmax into the reference library's fp64 entry point
+    (tests/golden/make_golden.py: joint_case).  Fresh random shapes here, beyond the committed fixtures."""
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/libwarprnnt.so not available")
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    rng = np.random.default_rng(20260924)
+    for _ in range(10):
+        B, T, U = int(rng.integers(1, 4)), int(rng.integers(1, 9)), int(rng.integers(1, 6))
+        V, H = int(rng.integers(2, 9)), int(rng.integers(1, 7))
+        k = mg.joint_case(rng, B, T, U, V, H, blank=int(rng.integers(0, V)), ragged=bool(rng.integers(0, 2)))
+        o64 = oracle.joint_loss_grad(*(k[n].astype(np.float64) for n in ("enc", "pred", "W", "b")), k["labels"],
+                                     k["input_lengths"], k["label_lengths"], int(k["blank"]), grad_scale=np.full(B, 1.0 / B))
+        assert np.allclose(o64["costs"], k["costs"], rtol=1e-10), (B, T, U, V, H)
+        for g in ("d_enc", "d_pred", "dW", "db"):
+            assert np.allclose(o64[g], k[g], rtol=1e-9, atol=1e-11), (g, B, T, U, V, H)
