@@ -6,8 +6,10 @@
 
 A "step" is one pass of the hot path (joint forward -> alpha/beta -> gradients to enc_acts, pred_acts,
 W, b) over one synthetic batch of the BASELINE C3 shape (B=32,T=512,U=128,V=1024,H=640 per GPU, bf16
-tensor-core path; --workload c2 runs the fp32 C2 shape).  Weak scaling: every rank holds a full
-batch; the only collective is ONE packed all-reduce of [loss_sum | dW | db] per step.
+tensor-core path; --workload c2 runs the fp32 C2 shape).  Default = weak scaling: every rank holds a full
+batch; --scaling strong = BASELINE C4 literally (ONE global batch of B utterances sharded over the ranks, 4 per GPU at
+N=8).  An N>1 weak run also measures the strong point and reports it under "strong".  The only collective is ONE
+packed all-reduce of [loss_sum | dW | db] per step.
 
 Printed JSON (one line, rank 0): see the task contract -- value (inputs resident in HBM), e2e (host
 buffers through the public torch API, H2D/D2H inside the timed region), roofline of the dominant
@@ -44,14 +46,27 @@ def peaks():
         return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def measured_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/rNN/traffic.json), or None."""
+def csrc_sha16():
+    """Hash of the CUDA sources: an ncu capture is only quoted next to a number when it was taken from THIS source."""
+    import glob
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(glob.glob(os.path.join(ROOT, "rnnt_speech_recognition_b200", "csrc", "*.cu*"))):
+        h.update(open(f, "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic():
+    """profiles/rNN/traffic.json = {"csrc_sha16": ..., "kernels": {name: dram bytes per launch}, "step": bytes} written by
+    tools/ncu_summary.py from an `ncu --set full` capture.  Returned only if it was captured from the current sources
+    (otherwise the figure would silently go stale the moment a kernel changes)."""
     import glob
     for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*", "traffic.json")), reverse=True):
         try:
-            t = json.load(open(f)).get(kernel)
-            if t:
-                return t["dram_bytes_per_launch"]
+            t = json.load(open(f))
+            if t.get("csrc_sha16") == csrc_sha16():
+                t["file"] = os.path.relpath(f, ROOT)
+                return t
         except Exception:
             pass
     return None
@@ -140,22 +155,26 @@ def cpu_reference_runner(cfg):
             def backward(ctx, go):
                 return ctx.grads.mul_(go.view(-1, 1, 1, 1)), None, None, None
 
-        def run(n):
+        def run(n, mb=4):
+            # micro-batches of `mb` utterances: utterances are independent (cpu_rnnt.h:290-301) and
+            # warp-transducer's OpenMP loop parallelises over the minibatch only, so a micro-batch gives it work while the
+            # (mb,T,U,V) slabs stay a few GB
             t0 = time.perf_counter()
             W, b = d["W"].clone().requires_grad_(), d["b"].clone().requires_grad_()
-            for i in range(n):   # one utterance at a time: the (T,U,V) slab is the only large temporary
-                j = i % B
-                e, p = d["enc"][j:j + 1].clone().requires_grad_(), d["pred"][j:j + 1].clone().requires_grad_()
+            for i0 in range(0, n, mb):
+                j = [(i0 + k) % B for k in range(min(mb, n - i0))]
+                e, p = d["enc"][j].clone().requires_grad_(), d["pred"][j].clone().requires_grad_()
                 z = torch.tanh(e[:, :, None, :] + p[:, None, :, :])
                 lp = torch.log_softmax(z @ W + b, -1)
-                c = RefLoss.apply(lp, d["labels"][j:j + 1].numpy(), d["il"][j:j + 1].numpy(), d["ll"][j:j + 1].numpy())
+                c = RefLoss.apply(lp, d["labels"][j].numpy(), d["il"][j].numpy(), d["ll"][j].numpy())
                 (c.sum() / B).backward()
             return time.perf_counter() - t0
-        return run, "reference", cores, "oracle/_ref/libwarprnnt.so (unmodified reference, OpenMP) + torch-CPU fp32 joint/autograd"
+        return run, "reference", cores, ("oracle/_ref/libwarprnnt.so (unmodified reference, OpenMP over the micro-batch) + "
+                                         "torch-CPU fp32 joint/autograd, micro-batches of 4 utterances")
 
     a = {k: v.numpy() for k, v in d.items()}
 
-    def run(n):
+    def run(n, mb=4):
         t0 = time.perf_counter()
         idx = [i % B for i in range(n)]
         oracle.joint_loss_grad(a["enc"][idx], a["pred"][idx], a["W"], a["b"], a["labels"][idx], a["il"][idx],
@@ -167,10 +186,12 @@ def cpu_reference_runner(cfg):
 def cpu_baseline(cfg, budget_s=20.0):
     run, kind, cores, note = cpu_reference_runner(cfg)
     t1 = run(1)                                     # warm-up + calibration
-    n = max(1, min(cfg["B"], int(budget_s / max(t1, 1e-3))))
-    t = run(n)
+    n = max(1, min(cfg["B"], 4 * max(1, int(budget_s / 3 / max(4 * t1, 1e-3)))))     # whole micro-batches of 4
+    reps = max(1, min(3, int(budget_s / max(n * t1, 1e-3))))
+    ts = [run(n) for _ in range(reps)]              # best of up to 3
+    t = min(ts)
     return {"value": n / t, "unit": "utt/s", "cores": cores, "kind": kind,
-            "sample": "%d utterance(s) of the workload shape, %.1f s; %s" % (n, t, note)}
+            "sample": "%d utterance(s) of the workload shape, best of %d runs (%.1f s each); %s" % (n, reps, t, note)}
 
 
 def reference_arm(args, cfg, rank):
@@ -180,6 +201,8 @@ def reference_arm(args, cfg, rank):
     t1 = run(1)
     total = args.steps + args.warmup
     n = max(1, min(cfg["B"], int(150.0 / (total * max(t1, 1e-3)))))
+    if n >= 4:
+        n -= n % 4                                  # whole micro-batches of 4 utterances
     for _ in range(args.warmup):
         run(n)
     times = [run(n) for _ in range(args.steps)]
@@ -189,19 +212,37 @@ def reference_arm(args, cfg, rank):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": val, "unit": "utt/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(cfg, args.gpus, args.workload),
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(cfg, args.gpus, args.workload, args.scaling),
         "cpu_baseline": {"value": val, "unit": "utt/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
 
 
-def workload_config(cfg, n_gpus, name):
-    return {"workload": "BASELINE %s: B=%d T=%d U=%d V=%d H=%d per GPU%s, joint fwd + alpha/beta + grads (d_enc,d_pred,dW,db)"
+def workload_config(cfg, n_gpus, name, scaling="weak"):
+    strong = scaling == "strong"
+    return {"workload": "BASELINE %s: B=%d T=%d U=%d V=%d H=%d %s%s, joint fwd + alpha/beta + grads (d_enc,d_pred,dW,db)"
                         % (name.upper(), cfg["B"], cfg["T"], cfg["U"], cfg["V"], cfg["H"],
+                           "GLOBAL batch sharded over the GPUs" if strong else "per GPU",
                            " (ragged T_b in [100,T], U_b in [10,U])" if cfg.get("ragged") else ""),
-            "global_batch": cfg["B"] * n_gpus, "parallelism": "dp%d" % n_gpus, "precision": cfg["precision"],
+            "global_batch": cfg["B"] * (1 if strong else n_gpus), "parallelism": "dp%d" % n_gpus, "precision": cfg["precision"],
             "l2": "256 MiB scratch write between timed steps; per-step working set (>4 GB) exceeds the 126 MB L2"}
+
+
+def op_path_block(pk):
+    """Materialised-logits entry (compute_rnnt_loss, the warp-transducer-compatible C ABI) on this GPU: ms per call,
+    achieved GB/s on SURVEY 8(d)'s algorithmic bytes 3*N*V*4 + 24*N against the measured HBM peak, and the reference's
+    own SIMT kernels (oracle/_ref/libwarprnnt_gpu.so, compiled unmodified for sm_100) on the same inputs."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    try:
+        import bench_op
+        out = []
+        for r in bench_op.run_shapes([(16, 256, 64, 256), (32, 512, 128, 1024)]):
+            r["frac_of_hbm_peak"] = r["rnnt_b200"]["GBps"] / pk["hbm_gbs"]
+            out.append(r)
+        return out
+    except Exception as e:                      # never let the secondary block take the headline line down
+        return {"error": repr(e)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -212,7 +253,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-op-path", action="store_true")
     ap.add_argument("--cpu-budget", type=float, default=20.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -240,24 +283,39 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
-    gB = B * world
-    d = synth(cfg, 1234 + rank, dev)
-    host = synth(cfg, 1234 + rank, dev, pin=True)
-    params = [d["W"].clone().requires_grad_(), d["b"].clone().requires_grad_()]
+
+    def shard(full, scaling):
+        """weak: this rank's own batch of B; strong: its contiguous shard of ONE global batch of B (run_rnnt.py:87-88)."""
+        if scaling == "weak":
+            return full, B * world
+        lo, hi = D.shard_bounds(B, world, rank)
+        return {k: (v[lo:hi].contiguous() if k in ("enc", "pred", "labels", "il", "ll") else v) for k, v in full.items()}, B
+
+    full_dev = synth(cfg, 1234 + (rank if args.scaling == "weak" else 0), dev)
+    d, gB = shard(full_dev, args.scaling)
+    host_full = synth(cfg, 1234 + (rank if args.scaling == "weak" else 0), dev, pin=True)
+    host = shard(host_full, args.scaling)[0]
+    host = {k: (v.pin_memory() if not v.is_pinned() else v) for k, v in host.items()}
+    params = [full_dev["W"].clone().requires_grad_(), full_dev["b"].clone().requires_grad_()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    mode = {"keep": None, "gB": gB}
 
     def step(enc, pred, labels, il, ll):
         enc.requires_grad_(), pred.requires_grad_()
         for p in params:
             p.grad = None
-        costs = rb.joint_rnnt_loss(enc, pred, params[0], params[1], labels, il, ll, precision=cfg["precision"])
+        costs = rb.joint_rnnt_loss(enc, pred, params[0], params[1], labels, il, ll, precision=cfg["precision"],
+                                   keep_activations=mode["keep"])
         loss_sum = costs.sum()
-        (loss_sum / gB).backward()                                   # run_rnnt.py:278
+        (loss_sum / mode["gB"]).backward()                           # run_rnnt.py:278
         ls, dW, db = D.allreduce_loss_and_weight_grads(loss_sum.detach(), params[0].grad, params[1].grad)
-        return ls / gB, enc.grad, pred.grad, dW, db
+        return ls / mode["gB"], enc.grad, pred.grad, dW, db
+
+    cur = {"d": d}
 
     def resident_step():
-        return step(d["enc"].detach(), d["pred"].detach(), d["labels"], d["il"], d["ll"])
+        x = cur["d"]
+        return step(x["enc"].detach(), x["pred"].detach(), x["labels"], x["il"], x["ll"])
 
     # e2e: every step copies ITS inputs from pinned host memory and reads its loss back.  The copy of step i+1 is
     # issued on a copy stream while step i computes (what a prefetching input pipeline does); the compute stream
@@ -313,6 +371,27 @@ def main():
     for _ in range(2):
         e2e_step()
     ms_e2e = timed(e2e_step, args.steps)
+    # the same step with NOTHING of size O(N*V) surviving the forward call (keep_activations = 0: the backward re-runs
+    # the projection chunk by chunk) -- the north-star-literal mode, reported beside the default
+    ms_nomat = None
+    if cfg["precision"] == "bf16":
+        mode["keep"] = False
+        for _ in range(2):
+            resident_step()
+        ms_nomat = timed(resident_step, args.steps)
+        mode["keep"] = None
+    # N > 1, weak run: also the BASELINE C4 strong-scaling point (one global batch of B sharded over the ranks)
+    strong = None
+    if world > 1 and args.scaling == "weak" and B >= world:
+        sd, sgB = shard(synth(cfg, 1234, dev), "strong")
+        cur["d"], mode["gB"] = sd, sgB
+        for _ in range(3):
+            resident_step()
+        ms_s = timed(resident_step, args.steps)
+        strong = {"value": sgB * args.steps / (ms_s * 1e-3), "unit": "utt/s", "ms_per_step": ms_s / args.steps,
+                  "global_batch": sgB, "utt_per_gpu": sgB / world, "scaling": "strong",
+                  "note": "BASELINE C4: B=%d sharded over %d GPUs, same step, max over ranks" % (sgB, world)}
+        cur["d"], mode["gB"] = d, gB
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=3)
@@ -328,7 +407,8 @@ def main():
 
     if rank == 0:
         pk, pk_src = peaks()
-        N = int((d["il"].long() * (d["ll"].long() + 1)).sum().item())      # valid lattice cells (== B*T*U when not ragged)
+        N = int((d["il"].long() * (d["ll"].long() + 1)).sum().item())      # valid lattice cells of this rank (== B*T*U when not ragged)
+        traffic = measured_traffic()
         if cfg["precision"] == "bf16":
             flops = 2.0 * N * H * V
             dom = next((k for k in kernels if k.endswith("<fwd>") or k.endswith("<fwd+keep>")), "joint_tc3_kernel<fwd+keep>")
@@ -336,7 +416,8 @@ def main():
             ach = flops / (t_dom * 1e-3) / 1e12 if t_dom else None
             peak = pk["bf16_tflops_sustained"]
             roof = {"kernel": dom, "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
-                    "frac": (ach / peak) if ach else None, "traffic": measured_traffic(dom),
+                    "frac": (ach / peak) if ach else None,
+                    "traffic": (traffic or {}).get("kernels", {}).get(dom),
                     "peak_source": "%s bf16 sustained (kernel timed inside the step)" % pk_src,
                     "algorithmic_flops_per_launch": flops, "launch_ms": t_dom,
                     "step": {"algorithmic_flops": 6.0 * N * H * V,
@@ -348,20 +429,34 @@ def main():
             byts = 24.0 * N
             ach = byts / (t_dom * 1e-3) / 1e9 if t_dom else None
             roof = {"kernel": dom, "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": (ach / pk["hbm_gbs"]) if ach else None, "traffic": measured_traffic(dom), "peak_source": pk_src,
+                    "frac": (ach / pk["hbm_gbs"]) if ach else None,
+                    "traffic": (traffic or {}).get("kernels", {}).get(dom), "peak_source": pk_src,
                     "algorithmic_bytes_per_launch": byts, "launch_ms": t_dom}
         h2d = sum(host[k].numel() * host[k].element_size() for k in ("enc", "pred", "labels", "il", "ll"))
         out = {
             "metric": METRIC, "value": gB * args.steps / (ms * 1e-3), "unit": "utt/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-            "config": workload_config(cfg, world, args.workload),
+            "scaling": args.scaling, "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": workload_config(cfg, world, args.workload, args.scaling),
             "clocks": sampler.summary() if sampler else None,
             "e2e": {"value": gB * args.steps / (ms_e2e * 1e-3), "unit": "utt/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps,
+                    "note": "inputs in (enc, pred, labels, lengths from pinned host memory), loss out (4 B); the gradients "
+                            "(d_enc, d_pred, dW, db) stay on the device where the optimizer / upstream autograd consumes them"},
             "gpu_launches": int(launches), "roofline": roof,
             "kernels_ms": {k: round(v, 4) for k, v in sorted(kernels.items(), key=lambda kv: -kv[1])},
         }
+        if ms_nomat is not None:
+            out["value_no_materialise"] = {"value": gB * args.steps / (ms_nomat * 1e-3), "unit": "utt/s",
+                                           "ms_per_step": ms_nomat / args.steps,
+                                           "note": "keep_activations=0: nothing of size O(N*V) survives the forward call; "
+                                                   "`value` is the default mode (forward keeps 2 B per logit for the backward)"}
+        out["dram_bytes_per_step"] = ({"value": traffic.get("step"), "source": traffic["file"] + " (ncu --set full of this "
+                                       "source tree, csrc_sha16 %s)" % traffic["csrc_sha16"]} if traffic else None)
+        if strong:
+            out["strong"] = strong
+        if world == 1 and not args.no_op_path and args.workload == "c3":
+            out["op_path"] = op_path_block(pk)
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(cfg, args.cpu_budget)
         sys.stdout.flush()

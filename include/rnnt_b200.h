@@ -10,9 +10,22 @@
  *
  *  Part 2 adds the entry points the reference has no analogue for: the fused joint-network +
  *  loss path (model.py:158-166 -> utils/loss.py:24-36 -> warp-transducer) in which the
- *  (B,T,U,V) logits are never written to HBM.  They follow the same conventions: status enum,
- *  caller-owned device workspace sized by a pure function, explicit CUstream, no allocation and
- *  no host synchronisation inside the library.
+ *  (B,T,U,V) fp32 logits are never written to HBM.  They follow the same conventions: status enum,
+ *  caller-owned device workspace sized by a pure function, explicit CUstream.  The Part 2 calls are
+ *  stream-ordered: no device allocation, no host synchronisation and no read-back (the only host
+ *  synchronisation in the library is the one the reference's contract mandates at the end of
+ *  compute_rnnt_loss: costs are host memory, gpu_rnnt.h:209-213).  State kept by the library:
+ *  a per-(device, kernel) flag that the >48 KB dynamic shared memory opt-in has been set
+ *  (mutex-protected; any number of devices and host threads per process), the launch counter and the
+ *  optional timing records of rnntb200_set_timing.
+ *
+ *  What reaches HBM on the tensor-core path (N = lattice cells, V vocabulary):
+ *    keep_activations = 0  forward: lse + two log-probs per cell, alpha, beta (O(N) floats).  The backward
+ *                          re-runs the projection per utterance chunk, leaving 2 bytes per logit (fp16 softmax
+ *                          numerators) + N*V/8 bytes of running maxima in the workspace for the two gradient
+ *                          GEMM kernels to consume; no (B,T,U,V) tensor is produced by the forward call.
+ *    keep_activations = 1  the forward itself writes those numerators (one pass fewer on the tensor cores).
+ *    In both modes the logit gradients, dZ and z = tanh(enc+pred) exist only in shared / tensor memory.
  *
  *  There is NO CPU implementation in this library: loc == RNNT_CPU returns
  *  RNNT_STATUS_EXECUTION_FAILED (and says so on stderr) instead of silently falling back.
@@ -119,30 +132,29 @@ rnntStatus_t rnntb200_loss_device(const float* activations, float* gradients, co
 
 typedef enum {
     RNNTB200_FP32_EXACT = 0, /**< fp32 CUDA-core arithmetic; parity gate rtol 1e-4 (BASELINE C1/C2) */
-    RNNTB200_BF16_TC = 1     /**< bf16 operands on tcgen05 tensor cores, fp32 accumulate (BASELINE C3-C5) */
+    RNNTB200_BF16_TC = 1     /**< 16-bit operands on tcgen05 tensor cores, fp32 accumulate (BASELINE C3-C5): the forward
+                                  projection runs on fp16 z / W (11-bit significands), the two gradient GEMMs on bf16 */
 } rnntb200Precision;
 
 /** Problem descriptor of the fused joint + loss path (model.py:158-166 hoisted form):
  *    z[b,t,u,:]  = tanh(enc[b,t,:] + pred[b,u,:])            model.py:158-163
  *    logits      = z . W + bias,  W is (H,V) row-major        model.py:165-166
  *    costs[b]    = RNN-T NLL of logits[b] (softmax inside)    utils/loss.py:24-36
- *  H % 64 == 0 and V % 64 == 0 are required by RNNTB200_BF16_TC. */
+ *  RNNTB200_BF16_TC requires H % 64 == 0, 64 <= H <= 768 and V % 64 == 0. */
 typedef struct {
     int B, maxT, maxU, H, V;
     int blank_label;
     int precision; /* rnntb200Precision */
     CUstream stream;
-    /** 0 (default): the library never synchronises with the host.  1: the bf16 backward may read
-     *  ONE int (the number of lattice tiles that intersect the valid region) back per utterance chunk, so that
-     *  ragged batches run their GEMMs over the valid rows only instead of the padded lattice. */
+    /** Reserved (ignored): round 1 let the backward read one int back to compact ragged batches; tiles are now
+     *  ranked on the device and the library never synchronises with the host.  Kept for struct layout stability. */
     int allow_host_sync;
-    /** 0: the backward recomputes the projection on the tensor cores (nothing but lse / log-prob pairs / alpha /
-     *  beta survives the forward).  1 (bf16 path): the forward also leaves, in the workspace, the softmax numerators
-     *  of every lattice cell as fp16 (2 bytes per logit) and the tanh outputs as bf16; the backward then forms the
-     *  logit gradients with one streaming pass instead of a second projection.  Set it when a backward call will
-     *  follow; it is honoured only when the whole batch fits one workspace chunk, otherwise (and for fp32) ignored.
-     *  Must have the same value in the forward and the backward call.  With allow_host_sync the one-int read-back
-     *  moves from the backward to the start of the forward. */
+    /** 0: nothing but lse / log-prob pairs / alpha / beta survives the forward; the backward re-runs the projection
+     *  chunk by chunk.  1 (tensor-core path): the forward also leaves, in the workspace, the softmax numerators of
+     *  every lattice cell as fp16 (2 bytes per logit) and their running maxima; the backward then skips its own
+     *  projection pass.  Set it when a backward call will follow; it is honoured only when the whole batch fits one
+     *  workspace chunk (<= 16 GiB of numerators), otherwise (and for fp32) ignored.  Must have the same value in the
+     *  forward and the backward call. */
     int keep_activations;
 } rnntb200JointDesc;
 
@@ -173,8 +185,19 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
 rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* enc, const float* pred,
                                    const float* W, const float* bias, float* logits, void* workspace);
 
-/** Number of kernels OF THIS LIBRARY launched in this process since load (bench.py's gpu_launches); the cuBLAS
- *  GEMM calls of the bf16 backward are not included. */
+/** Greedy-decode joint (utils/decoding.py:6-18, called per step at :69-78): one lattice cell per batch row,
+ *    logits[b,:] = tanh((f[b,:] + g[b,:]) . K1 + b1) . K2 + b2;  best[b] = argmax_v logits (smallest index among equal
+ *    maxima, as tf.argmax);  best_logp[b] = log_softmax(logits[b])[best[b]]
+ *  in ONE launch (thread-block clusters of 8 CTAs per row; fp32 FMA arithmetic).  f, g: (B,P) device rows with strides
+ *  ldf, ldg (so f = encoded[:, i, :] and g = pred_out[:, -1, :] need no copy); K1 (P,H) and b1 (H) are Keras Dense-1
+ *  (K1 == NULL: f, g are the already projected activations, P == H); K2 (H,V), b2 (V).  Any of logits (B,V), best (B),
+ *  best_logp (B) may be NULL, not all.  P <= 4096, H <= 2048. */
+rnntStatus_t rnntb200_joint_step(const float* f, long long ldf, const float* g, long long ldg, const float* K1,
+                                 const float* b1, const float* K2, const float* b2, int B, int P, int H, int V,
+                                 float* logits, int* best, float* best_logp, CUstream stream);
+
+/** Number of kernels launched by this library in this process since load (bench.py's gpu_launches).  Every kernel
+ *  on the path is the library's own: it links no GEMM library. */
 unsigned long long rnntb200_launch_count();
 
 /** Per-kernel CUDA-event instrumentation for bench.py's attribution pass.  set_timing(1) clears the record

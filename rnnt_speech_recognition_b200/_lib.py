@@ -28,7 +28,7 @@ class JointDesc(C.Structure):
 
 EXPORTS = ("get_warprnnt_version", "rnntGetStatusString", "get_workspace_size", "compute_rnnt_loss",
            "compute_rnnt_loss_fp64", "rnntb200_loss_device", "rnntb200_joint_workspace_size",
-           "rnntb200_joint_loss_forward", "rnntb200_joint_loss_backward", "rnntb200_joint_logits",
+           "rnntb200_joint_loss_forward", "rnntb200_joint_loss_backward", "rnntb200_joint_logits", "rnntb200_joint_step",
            "rnntb200_launch_count", "rnntb200_build_info", "rnntb200_set_timing", "rnntb200_get_timing")
 
 _lib = None
@@ -50,8 +50,6 @@ def load(build_if_missing=True):
             if not os.path.exists(SO):
                 raise
     if not os.path.exists(SO):
-                raise
-    if not os.path.exists(SO):
         raise RuntimeError("librnnt_b200.so is missing: run `python -m rnnt_speech_recognition_b200.build` "
                            "(there is no CPU fallback)")
     L = C.CDLL(SO)
@@ -67,6 +65,7 @@ def load(build_if_missing=True):
     L.rnntb200_joint_loss_forward.argtypes = [C.POINTER(JointDesc)] + [vp] * 9
     L.rnntb200_joint_loss_backward.argtypes = [C.POINTER(JointDesc)] + [vp] * 13
     L.rnntb200_joint_logits.argtypes = [C.POINTER(JointDesc)] + [vp] * 6
+    L.rnntb200_joint_step.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
     L.rnntb200_launch_count.restype = C.c_ulonglong
     L.rnntb200_build_info.restype = C.c_char_p
     L.rnntb200_set_timing.argtypes = [ci]

@@ -8,8 +8,8 @@ import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rnnt_b200.cu")
-OUT = os.path.join(HERE, "librnnt_b200.so")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels_simt.cuh", "joint_tc.cuh", "joint_tc2.cuh", "joint_tc3.cuh", "ptx.cuh", "bwd_gemm.cuh", "timing.cuh", "mma_probe.cuh")] + [
+OUT = os.environ.get("RNNTB200_BUILD_OUT") or os.path.join(HERE, "librnnt_b200.so")
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels_simt.cuh", "joint_tc.cuh", "joint_tc3.cuh", "bwd_tc.cuh", "ptx.cuh", "timing.cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "rnnt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]
@@ -35,8 +35,6 @@ def build(force=False, verbose=False):
     flags = list(NVCC_FLAGS)
     if os.environ.get("RNNTB200_NO_TC") == "1":      # bring-up switch: CUDA-core kernels only
         flags += ["-DRNNTB200_NO_TC"]
-    else:
-        flags += ["-lcublas", "-Xlinker", "-rpath,/usr/local/cuda/lib64"]
     cmd = [nvcc()] + flags + (["-Xptxas", "-v"] if verbose else []) + [SRC, "-o", OUT + ".tmp"]
     env = dict(os.environ)
     env.pop("CC", None)

@@ -1,33 +1,50 @@
-// joint_tc3.cuh -- third-generation fused joint kernel = joint_tc2 (z resident in TENSOR MEMORY, deep W ring,
-// whole-stage MMA issue) + TMA-fed producers.
+// joint_tc3.cuh -- the fused joint FORWARD kernel (model.py:158-166 + the log-softmax and
+// gather of gpu_rnnt.h:73-80 / gpu_rnnt_kernel.h:5-9), generation 3: the A operand z = tanh(enc + pred) lives in
+// TENSOR MEMORY as fp16, W^T (fp16) streams through a deep TMA ring, whole-stage MMA issue, TMA-fed producers.
 //
-// v2's producers (coalesced global loads -> tanh -> smem staging -> 256-thread barrier -> re-read own row ->
-// tcgen05.st) took ~2.1 k cycles per K block, and because z is single-buffered in TMEM that chain gates the first
-// V-chunk of every tile (measured: 1.2 ms of a 3.8 ms kernel).  Here a dedicated warp TMA-loads the tile's
-// pred rows (box [32 fp32 x UU rows], SWIZZLE_128B) and enc rows (box [64 x TT]) K block by K block into a
-// ring, RUNNING AHEAD across tiles; each producer thread then reads ITS OWN lattice row straight from shared
-// memory (conflict-free), applies tanh, packs to bf16 and writes its TMEM lane with tcgen05.st -- no staging
-// pass, no inter-warp barrier, no register prefetch buffers.
+// A dedicated warp TMA-loads the tile's pred rows (box [32 fp32 x UU rows], SWIZZLE_128B) and enc rows (box [64 x TT])
+// K block by K block into a ring, RUNNING AHEAD across tiles; each producer thread reads ITS OWN lattice row straight
+// from shared memory (conflict-free), applies tanh, packs to fp16 and writes its TMEM lane with tcgen05.st -- no
+// staging pass, no inter-warp barrier, no register prefetch buffers.
+//
+// Operand format: fp16 (same tcgen05.mma.kind::f16 rate as bf16, 11-bit instead of 8-bit significand): z is in
+// [-1, 1] and W ~ 1/sqrt(H), both far inside the fp16 range; tanh is evaluated to fp32 accuracy (ex2 + rcp) so that
+// the operand rounding (2^-12) is the only error of the logits.
 //
 // Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
 //
 // MODE 0  forward: lse + (blank, label) log-probs per cell; nothing else leaves the SM
-// MODE 1  recompute backward: same mainloop, epilogue writes the bf16 logit gradients, producers the bf16 z rows
-// MODE 2  forward that KEEPS its activations (rnntb200JointDesc.keep_activations): MODE 0 + the fp16 softmax
-//         numerators 2^(y - m) the epilogue computes anyway, the running maxima m, and the bf16 z rows;
-//         dl_from_kept_kernel (below) then turns the numerators into logit gradients in one streaming pass.
+// MODE 2  forward that KEEPS its activations (rnntb200JointDesc.keep_activations, and the backward's per-chunk
+//         recompute): MODE 0 + the fp16 softmax numerators 2^(y - m) the epilogue computes anyway and the running
+//         maxima m per 32-column group; bwd_tc.cuh turns them into logit gradients inside its GEMM prologues.
 #pragma once
 #include <cuda_fp16.h>
-#include "joint_tc2.cuh"
+#include "joint_tc.cuh"
 
 namespace rb {
 
 constexpr int TC3_THREADS = 480;
 constexpr int TC3_IN_STAGES = 2;
+constexpr int TC2_NC = 64;             // vocabulary columns per accumulator buffer / W^T chunk
+constexpr int TC2_MAX_STAGES = 24;
+constexpr int TC2_MAX_NBUF = 4;
 
+// z occupies H/2 TMEM columns (two fp16 per 32-bit column), the rest holds `nbuf` 64-column fp32 accumulators.
+// One W stage = ks K-blocks ([64 v x 64 k] boxes, 8 KB each): the MMA thread pays one mbarrier wait and one commit per
+// 4*ks MMAs (with ks = 1 the single issuing thread, not the tensor pipe, set the pace: 123 k cycles per tile measured).
+struct Tc2Geom { int nbuf, stages, zcols, ks; size_t smem_bytes; bool ok; };
 inline Tc2Geom tc3_geometry(int H, int V) {
-    Tc2Geom g = tc2_geometry(H, V);
-    if (!g.ok) return g;
+    Tc2Geom g{};
+    if (H % 64 || V % 64 || H < 64) return g;
+    g.zcols = (H / 64) * 32;
+    const int acc_cols = TC_TMEM_COLS - g.zcols;
+    g.nbuf = acc_cols / TC2_NC;
+    if (g.nbuf > TC2_MAX_NBUF) g.nbuf = TC2_MAX_NBUF;
+    if (g.nbuf < 2) return g;
+    const int KB = H / 64;
+    g.ks = 1;
+    for (int k = 5; k >= 1; --k)
+        if (KB % k == 0) { g.ks = k; break; }   // largest divisor of KB that is <= 5: stages are never partial
     // smem: enc/pred ring (2 x (2 x 16 KB pred boxes + 4 KB enc box)) + W ring; W stages shrink to fit
     const size_t in_bytes = (size_t)TC3_IN_STAGES * (2 * 16384 + 4096);
     const size_t bias_bytes = V <= 4096 ? (size_t)V * 4 : 0;
@@ -127,7 +144,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         // barrier addresses then stay in uniform registers.  (Issuing from inside `if (lane == 0)` made every
         // operand a vector register that had to be moved to the uniform datapath per instruction -- measured
         // 117 cycles per N=64 MMA instead of the 32-cycle dispatch floor.)
-        const uint32_t idesc = ptx::umma_idesc_bf16(128, NC);
+        const uint32_t idesc = ptx::umma_idesc_f16(128, NC);
         int stage = 0; uint32_t phase = 0, g = 0, it = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             if (!decode_tile(p, tile).valid) continue;
@@ -195,28 +212,14 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         }
     } else if (warp >= 4 && warp < 12) {
         // ===================== producers (warps 4-11): thread = (lattice row r2 = TMEM lane, k-half hh) =====================
-        const int pw = warp - 4, ptid = threadIdx.x - 128;
+        const int pw = warp - 4;
         const int q4 = pw & 3, hh = pw >> 2, r2 = q4 * 32 + lane;
+        const bool fast_tanh = (p.dbg & 512) != 0;
         uint32_t it = 0; int st = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
             if (p.dbg & 8) continue;
-            if (!ti.valid) {
-                if (MODE != 0 && !p.slot) {  // uncompacted rows: the plain GEMMs reduce over ALL rows, padding tiles must read as zero
-                    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-                    if (MODE == 1) {         // (MODE 2: dl_from_kept_kernel zero-fills the dlogits rows of padding tiles)
-                        uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
-                        for (int i = ptid; i < 128 * p.V / 8; i += 256) d4[i] = z4;
-                    }
-                    if (p.zb) {
-                        const int h8 = p.H / 8 + 1;   // + the 8 columns at H (ones column): the dW GEMM reads H + 8 columns
-                        for (int i = ptid; i < 128 * h8; i += 256)
-                            *reinterpret_cast<uint4*>(p.zb + ((size_t)tile * 128 + i / h8) * p.zld + (i % h8) * 8) = z4;
-                    }
-                }
-                continue;
-            }
-            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
+            if (!ti.valid) continue;
             const int tl = r2 / p.UU, ul = r2 % p.UU;   // row of the enc box / of the pred box
             const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
             for (int kb = 0; kb < KB; ++kb) {
@@ -229,9 +232,12 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 for (int c = 0; c < 8; ++c) {
                     const float4 q = *reinterpret_cast<const float4*>(prow + ((c ^ (ul & 7)) << 4));
                     const float4 e = *reinterpret_cast<const float4*>(erow + (c << 4));
-                    if (ok) {   // (tanh.approx.bf16x2 / f16x2 lower to two scalar MUFU ops on sm_100a: no gain from packing)
-                        zr[c * 2 + 0] = ptx::pack_bf16x2(ptx::tanh_approx(e.x + q.x), ptx::tanh_approx(e.y + q.y));
-                        zr[c * 2 + 1] = ptx::pack_bf16x2(ptx::tanh_approx(e.z + q.z), ptx::tanh_approx(e.w + q.w));
+                    if (ok && !fast_tanh) {
+                        zr[c * 2 + 0] = ptx::pack_f16x2(ptx::tanh_accurate(e.x + q.x), ptx::tanh_accurate(e.y + q.y));
+                        zr[c * 2 + 1] = ptx::pack_f16x2(ptx::tanh_accurate(e.z + q.z), ptx::tanh_accurate(e.w + q.w));
+                    } else if (ok) {   // RNNTB200_DBG bit 512: tanh.approx (one MUFU op instead of two, 2^-11 relative) -- A/B switch
+                        zr[c * 2 + 0] = ptx::pack_f16x2(ptx::tanh_approx(e.x + q.x), ptx::tanh_approx(e.y + q.y));
+                        zr[c * 2 + 1] = ptx::pack_f16x2(ptx::tanh_approx(e.z + q.z), ptx::tanh_approx(e.w + q.w));
                     } else {
                         zr[c * 2 + 0] = 0u; zr[c * 2 + 1] = 0u;
                     }
@@ -239,15 +245,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
                 if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
-                if (MODE != 0 && p.zb) {
-                    __nv_bfloat16* zdst = p.zb + (rowbase + r2) * p.zld + kb * 64 + hh * 32;   // 64 bytes of this thread's row
-                    ptx::st_global_256(zdst, zr);
-                    ptx::st_global_256(zdst + 16, zr + 8);
-                    // the ones column at index H that turns the dW GEMM's extra output row into db (written once per row,
-                    // by the thread that owns the row's last 32 columns)
-                    if (kb == KB - 1 && hh == 1)
-                        *reinterpret_cast<uint4*>(p.zb + (rowbase + r2) * p.zld + p.H) = make_uint4(0x00003F80u, 0u, 0u, 0u);
-                }
                 if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);   // previous tile's MMAs have retired: z columns reusable
                 ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zr);
                 ptx::tmem_st_wait();
@@ -271,11 +268,6 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             const int lab = (rv && u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
             const long long cell = ((long long)ti.b * p.maxT + t) * p.maxU + u;
             float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f;
-            float kd2 = -CUDART_INF_F, cg = 0.f, csb = 0.f, csl = 0.f;
-            if (MODE == 1 && rv) {
-                const float4 cf = p.coef[cell];
-                kd2 = cf.x * LOG2E; cg = cf.y; csb = cf.z; csl = cf.w;
-            }
             const uint32_t lane_addr = acc0 + ((uint32_t)(warp * 32) << 16);
             for (int c = 0; c < NCH; ++c, ++g) {
                 const uint32_t buf = g % NBUF, use = g / NBUF;
@@ -294,7 +286,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
-                    if (MODE != 1) {
+                    {
                         float gm = y[0];
 #pragma unroll
                         for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
@@ -341,26 +333,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                             const float s2a = (d & 8) ? s4[1] : s4[0], s2b = (d & 8) ? s4[3] : s4[2];
                             if (mine) yl = (d & 16) ? s2b : s2a;
                         }
-                    } else {
-                        uint32_t o[16];
-#pragma unroll
-                        for (int i = 0; i < 32; i += 2)
-                            o[i >> 1] = ptx::pack_bf16x2(cg * ptx::ex2_approx(y[i] + kd2), cg * ptx::ex2_approx(y[i + 1] + kd2));
-                        __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
-                        ptx::st_global_256(dst, o);
-                        ptx::st_global_256(dst + 16, o + 8);
                     }
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
             }
-            if (MODE == 1 && rv) {   // the two special columns: final values precomputed by cell_coef_kernel
-                __nv_bfloat16* drow = p.dl + (rowbase + r) * p.V;
-                drow[p.blank] = __float2bfloat16(csb);
-                if (lab >= 0) drow[lab] = __float2bfloat16(csl);
-            }
-            if (MODE != 1 && rv) {
+            if (rv && p.lse) {   // (lse == NULL: a backward-time recompute that only wants the kept activations)
                 const float lse2 = m2 + log2f(s);
                 p.lse[cell] = lse2 * LN2;
                 const long long k = sk_index(ti.b, t, u, p.maxU, p.SK);
@@ -375,92 +354,13 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 }
 
 
-// Backward of a forward that kept its activations (MODE 2): dlogits[row, v] = e[row, v] * g * 2^(gm[row, v/32] + kd)
-// with e the kept fp16 numerators -- a pure streaming pass (2 bytes in, 2 bytes out per logit, IN PLACE: the bf16
-// result overwrites the fp16 input) instead of a second projection on the tensor cores.  The two special columns
-// (blank, label) receive their precomputed final values afterwards, from the thread that wrote that 16-byte vector.
-//   grid = tiles of the launch (original order), block = 256: warp <-> row (16 rows each), lane <-> 16-byte vectors.
-__device__ __forceinline__ void st_bf16_after(__nv_bfloat16* ptr, float val) {
-    // a 2-byte store that the compiler may not move across the surrounding (differently typed) vector accesses;
-    // same thread + same address, so the hardware keeps it after the 16-byte store it patches
-    asm volatile("st.global.b16 [%0], %1;" :: "l"(ptr), "h"(__bfloat16_as_ushort(__float2bfloat16(val))) : "memory");
-}
-__global__ void __launch_bounds__(256) dl_from_kept_kernel(const JointTcParams p) {
-    constexpr float LOG2E = 1.4426950408889634f;
-    const int tile = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nvec = p.V >> 3;
-    const TileInfo ti = decode_tile(p, tile);
-    const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-    if (!ti.valid) {
-        if (!p.slot) {   // uncompacted rows: padding tiles must read as zero in the GEMMs
-            uint4* d4 = reinterpret_cast<uint4*>(p.dl + (size_t)tile * 128 * p.V);
-            for (int i = threadIdx.x; i < 128 * nvec; i += 256) d4[i] = z4;
-        }
-        return;
-    }
-    const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;
-    // the tile's maxima [group][row] (coalesced in global) are staged as [row][group] (+1 word of padding per row:
-    // conflict-free both ways) so that a row's lanes read consecutive words
-    extern __shared__ float gm_s[];
-    const int G = p.V >> 5;
-    {
-        const float* gsrc = p.gm + rowbase * (size_t)G;
-        for (int i = threadIdx.x; i < G * 128; i += 256) gm_s[(i & 127) * (G + 1) + (i >> 7)] = gsrc[i];
-    }
-    __syncthreads();
-    for (int r = warp; r < 128; r += 8) {
-        const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
-        const bool rv = t < ti.Tn && u < ti.Un;
-        uint4* row4 = reinterpret_cast<uint4*>(p.dl + (rowbase + r) * p.V);
-        if (!rv) {
-            for (int v = lane; v < nvec; v += 32) row4[v] = z4;
-            continue;
-        }
-        const float4 cf = p.coef[((long long)ti.b * p.maxT + t) * p.maxU + u];
-        const float kd2 = cf.x * LOG2E, cg = cf.y;
-        const int lab = (u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
-        const float* gmr = gm_s + r * (G + 1);
-        for (int v0 = lane; v0 < nvec; v0 += 128) {
-            uint4 x[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)                     // four independent 16-byte requests per lane before any use
-                if (v0 + 32 * k < nvec) x[k] = row4[v0 + 32 * k];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int v = v0 + 32 * k;
-                if (v < nvec) {
-                    const float sc = cg * ptx::ex2_approx(gmr[v >> 2] + kd2);
-                    const uint32_t w[4] = {x[k].x, x[k].y, x[k].z, x[k].w};
-                    uint32_t o[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        float f0, f1;
-                        ptx::unpack_f16x2(w[i], f0, f1);
-                        o[i] = ptx::pack_bf16x2(f0 * sc, f1 * sc);
-                    }
-                    row4[v] = make_uint4(o[0], o[1], o[2], o[3]);
-                }
-            }
-        }
-        // the two special columns, patched by the lane that wrote their vector (vector index & 31 == lane)
-        __nv_bfloat16* drow = reinterpret_cast<__nv_bfloat16*>(row4);
-        if (((p.blank >> 3) & 31) == lane) st_bf16_after(drow + p.blank, cf.z);   // (label == blank: cf.w == cf.z)
-        if (lab >= 0 && ((lab >> 3) & 31) == lane) st_bf16_after(drow + lab, cf.w);
-    }
-}
-
 template <int MODE>
 inline rnntStatus_t tc3_launch(const Tc2Geom& g3, const CUtensorMap& tm, const CUtensorMap& tmp, const CUtensorMap& tme,
                                const JointTcParams& p, cudaStream_t s) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(joint_tc3_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)232448) != cudaSuccess)
-            return RNNT_STATUS_EXECUTION_FAILED;
-        attr_set = true;
-    }
+    if (!tc_smem_optin(reinterpret_cast<const void*>(joint_tc3_kernel<MODE>))) return RNNT_STATUS_EXECUTION_FAILED;
     const int ntiles = p.nb * p.nTb * p.nUb;
     const int grid = ntiles < tc_num_sms() ? ntiles : tc_num_sms();
-    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : MODE == 1 ? "joint_tc3_kernel<dlogits>" : "joint_tc3_kernel<fwd+keep>", s);
+    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : "joint_tc3_kernel<fwd+keep>", s);
     joint_tc3_kernel<MODE><<<grid, TC3_THREADS, g3.smem_bytes, s>>>(tm, tmp, tme, p);
     return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
 }

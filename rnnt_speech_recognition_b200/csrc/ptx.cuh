@@ -107,6 +107,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// same, A = B = fp16 (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major = 0, int b_mn_major = 0) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
 // D[tmem] (+)= A[smem] . B[smem]^T ; single-thread issue
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -166,6 +172,15 @@ __device__ __forceinline__ float tanh_approx(float x) {
     float y;
     asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+}
+// tanh to fp32 accuracy on the MUFU units: 1 - 2 / (1 + 2^(2 log2(e) |x|)), sign restored.  ex2.approx (2 ulp) and
+// rcp.approx (1 ulp) leave an ABSOLUTE error of ~1e-7, an order of magnitude below the fp16 rounding of the result
+// (tanh.approx.f32 alone is only good to 2^-11 relative, i.e. coarser than the fp16 operand it would feed).
+__device__ __forceinline__ float tanh_accurate(float x) {
+    float t, r;
+    asm("ex2.approx.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * 2.8853900817779268f));   // +inf for |x| > 44: r = 0, result 1
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(1.f + t));
+    return copysignf(fmaf(-2.f, r, 1.f), x);
 }
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;

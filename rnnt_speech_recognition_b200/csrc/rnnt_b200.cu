@@ -6,14 +6,16 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdint>
+#include <cmath>
+#include <vector>
 
 #include <cuda_runtime.h>
 
 #include "kernels_simt.cuh"
 #include "timing.cuh"
+#include "joint_step.cuh"
 #ifndef RNNTB200_NO_TC
 #include "joint_tc.cuh"
-#include "mma_probe.cuh"
 #endif
 
 namespace {
@@ -43,13 +45,15 @@ struct LossWs {
     }
 };
 
-__global__ void negate_kernel(const float* __restrict__ in, float* __restrict__ out, int n) {
+// costs[b] = -llForward[b] (cpu_rnnt.h:172), with the reference's consistency guard of the two lattice passes
+// (cpu_rnnt.h:166-170: "WARNING: Forward backward likelihood mismatch" when |llForward - llBackward| > 0.1) as a
+// device-side printf: stream-ordered, costs nothing unless it fires, and needs no read-back.
+__global__ void finish_costs_kernel(const float* __restrict__ llf, const float* __restrict__ llb, float* __restrict__ out, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = -in[i];
-}
-__global__ void negate_kernel(const double* __restrict__ in, double* __restrict__ out, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = -in[i];
+    if (i >= n) return;
+    out[i] = -llf[i];
+    const float diff = fabsf(llf[i] - llb[i]);
+    if (diff > 0.1f) printf("WARNING: Forward backward likelihood mismatch %f (utterance %d)\n", diff, i);
 }
 
 inline rnntStatus_t check_launch() { return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED; }
@@ -127,12 +131,18 @@ rnntStatus_t compute_impl(const T* acts, T* grads, const int* labels, const int*
     rnntStatus_t st = loss_op<T>(acts, grads, labels, ylen, xlen, nullptr, V, B, opt.maxT, opt.maxU, opt.blank_label,
                                  workspace, s);
     if (st) return st;
-    // costs to HOST + sync + negate, as gpu_rnnt.h:209-213
+    // costs to HOST + sync + negate, as gpu_rnnt.h:209-213; llBackward comes along for the guard of cpu_rnnt.h:166-170
     LossWs<T> w(workspace, B, opt.maxT, opt.maxU);
-    if (cudaMemcpyAsync(costs_host, w.llf, sizeof(T) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    std::vector<T> llb((size_t)B);
+    if (cudaMemcpyAsync(costs_host, w.llf, sizeof(T) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(llb.data(), w.llb, sizeof(T) * B, cudaMemcpyDeviceToHost, s) != cudaSuccess)
         return RNNT_STATUS_MEMOPS_FAILED;
     if (cudaStreamSynchronize(s) != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
-    for (int i = 0; i < B; ++i) costs_host[i] = -costs_host[i];
+    for (int i = 0; i < B; ++i) {
+        const double diff = fabs((double)costs_host[i] - (double)llb[i]);
+        if (diff > 0.1) printf("WARNING: Forward backward likelihood mismatch %f\n", diff);   // cpu_rnnt.h:167-170
+        costs_host[i] = -costs_host[i];
+    }
     return RNNT_STATUS_SUCCESS;
 }
 
@@ -335,7 +345,7 @@ rnntStatus_t rnntb200_loss_device(const float* activations, float* gradients, co
                                      workspace, s);
     if (st) return st;
     LossWs<float> w(workspace, minibatch, options.maxT, options.maxU);
-    negate_kernel<<<(minibatch + 127) / 128, 128, 0, s>>>(w.llf, costs_device, minibatch);
+    finish_costs_kernel<<<(minibatch + 127) / 128, 128, 0, s>>>(w.llf, w.llb, costs_device, minibatch);
     RB_LAUNCHED(1);
     return check_launch();
 }
@@ -374,7 +384,7 @@ rnntStatus_t rnntb200_joint_loss_forward(const rnntb200JointDesc* desc, const fl
     if (st) return st;
     st = launch_alpha_beta(ws.loss, input_lengths, label_lengths, d.B, d.maxT, d.maxU, s);
     if (st) return st;
-    negate_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.loss.llf, costs, d.B);
+    finish_costs_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.loss.llf, ws.loss.llb, costs, d.B);
     RB_LAUNCHED(1);
     return check_launch();
 }
@@ -403,8 +413,8 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
     RB_LAUNCHED(1);
     if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     unsigned nl = 0;
-    rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, W, bias, labels, label_lengths, input_lengths,
-                                      ws.loss.lse, ws.coef, d_enc, d_pred, dW, db, s, &nl, d.allow_host_sync != 0);
+    rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, bias, labels, label_lengths, input_lengths, ws.coef, d_enc,
+                                      d_pred, dW, db, s, &nl);
     RB_LAUNCHED(nl);
     return st;
 #else
@@ -432,14 +442,22 @@ rnntStatus_t rnntb200_joint_logits(const rnntb200JointDesc* desc, const float* e
     return RNNT_STATUS_SUCCESS;
 }
 
-#ifndef RNNTB200_NO_TC
-// bring-up probe (not part of the public header): cycles per tcgen05.mma, see csrc/mma_probe.cuh
-int rnntb200_debug_mma_probe(int variant, int iters, int ctas, float* out_dev) {
-    cudaFuncSetAttribute(rb::mma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    rb::mma_probe_kernel<<<ctas, 128, 100 * 1024>>>(variant, iters, out_dev);
-    return (int)cudaDeviceSynchronize();
+rnntStatus_t rnntb200_joint_step(const float* f, long long ldf, const float* g, long long ldg, const float* K1,
+                                 const float* b1, const float* K2, const float* b2, int B, int P, int H, int V,
+                                 float* logits, int* best, float* best_logp, CUstream stream) {
+    if (!f || !g || !K2 || B <= 0 || P <= 0 || H <= 0 || V <= 0 || (!logits && !best && !best_logp)) return RNNT_STATUS_INVALID_VALUE;
+    if (!K1 && P != H) return RNNT_STATUS_INVALID_VALUE;
+    if (P > rb::STEP_MAX_DIM || H > rb::STEP_CLUSTER * rb::STEP_THREADS || V > (1 << 20)) {
+        fprintf(stderr, "rnnt_b200: rnntb200_joint_step supports P <= %d, H <= %d\n", rb::STEP_MAX_DIM, rb::STEP_CLUSTER * rb::STEP_THREADS);
+        return RNNT_STATUS_INVALID_VALUE;
+    }
+    rb::StepParams p{f, g, ldf, ldg, K1, b1, K2, b2, B, P, H, V, logits, best, best_logp};
+    const size_t smem = rb::joint_step_smem(P, H, V);
+    if (smem > 48 * 1024 && !rb::tc_smem_optin(reinterpret_cast<const void*>(rb::joint_step_kernel))) return RNNT_STATUS_EXECUTION_FAILED;
+    rb::joint_step_kernel<<<B * rb::STEP_CLUSTER, rb::STEP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+    RB_LAUNCHED(1);
+    return check_launch();
 }
-#endif
 
 unsigned long long rnntb200_launch_count() { return g_launches.load(); }
 

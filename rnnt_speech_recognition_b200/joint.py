@@ -18,7 +18,7 @@ import torch
 from . import _lib
 from .loss import encoder_lengths
 
-__all__ = ["joint_rnnt_loss", "joint_logits", "Joint", "get_fused_loss_fn"]
+__all__ = ["joint_rnnt_loss", "joint_logits", "joint_step", "Joint", "get_fused_loss_fn"]
 
 _PREC = {"fp32": _lib.FP32_EXACT, "bf16": _lib.BF16_TC, _lib.FP32_EXACT: _lib.FP32_EXACT, _lib.BF16_TC: _lib.BF16_TC}
 
@@ -27,13 +27,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _desc(B, T, U, H, V, blank, precision, compact=True, keep=False):
-    # torch callers synchronise with the host every step anyway (loss read-back), so the torch surface lets the
-    # backward compact ragged batches (one 4-byte read-back); capture-safe callers pass compact=False.
-    sync_ok = 1 if (compact and os.environ.get("RNNTB200_COMPACT", "1") != "0"
-                    and not torch.cuda.is_current_stream_capturing()) else 0
+def _desc(B, T, U, H, V, blank, precision, keep=False):
+    # (call inside `with torch.cuda.device(...)`: the stream is the CURRENT stream of the tensors' device)
     return _lib.JointDesc(B, T, U, H, V, int(blank), _PREC[precision],
-                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, sync_ok, 1 if keep else 0)
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, 0, 1 if keep else 0)
 
 
 def _workspace(desc, device):
@@ -78,7 +75,7 @@ class _JointRNNT(torch.autograd.Function):
         with torch.cuda.device(enc.device):
             # a backward will follow: let the forward keep its softmax numerators / tanh outputs in the workspace
             keep = any(ctx.needs_input_grad[:4]) if keep is None else bool(keep)
-            desc = _desc(B, T, U, H, V, blank, precision, compact, keep)
+            desc = _desc(B, T, U, H, V, blank, precision, keep)
             ws = _workspace(desc, enc.device)
             costs = torch.empty(B, dtype=torch.float32, device=enc.device)
             st = L.rnntb200_joint_loss_forward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
@@ -96,7 +93,7 @@ class _JointRNNT(torch.autograd.Function):
         g = grad_costs.to(torch.float32).contiguous()
         d_enc, d_pred, dW, db = (torch.empty_like(t) for t in (enc, pred, W, b))
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.compact, ctx.keep)
+            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.keep)
             st = L.rnntb200_joint_loss_backward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                 _ptr(label_lengths), _ptr(input_lengths), _ptr(g), _ptr(d_enc),
                                                 _ptr(d_pred), _ptr(dW), _ptr(db), _ptr(ctx.ws))
@@ -109,13 +106,13 @@ def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_leng
                     compact=True, keep_activations=None):
     """Per-utterance RNN-T NLL (B,) of logits = tanh(enc_acts[:,:,None]+pred_acts[:,None]) @ W + b,
     differentiable w.r.t. enc_acts, pred_acts, W, b -- without ever materialising (B,T,U,V).
-    precision: 'bf16' (tcgen05 tensor cores, fp32 accumulate) or 'fp32' (exact CUDA-core path).
-    compact: let the bf16 backward skip padding tiles of ragged batches (one 4-byte host read-back per chunk);
-    pass False for a fully sync-free call (stream capture of the whole step is not validated yet, tools/graph_capture.py).
-    keep_activations: None = automatically when a gradient is required (the bf16 forward then leaves its softmax
-    numerators (fp16) and tanh outputs in the workspace and the backward is one streaming pass + two GEMMs);
-    False = the backward recomputes the projection on the tensor cores (2 bytes per logit less workspace traffic,
-    one more tensor-core pass)."""
+    precision: 'bf16' = the tensor-core path (tcgen05, 16-bit operands, fp32 accumulate) or 'fp32' (exact CUDA-core path).
+    compact: accepted for compatibility and ignored -- ragged batches are compacted on the device, the library never
+    synchronises with the host.
+    keep_activations: None = automatically when a gradient is required (the forward then leaves its softmax
+    numerators (fp16, 2 bytes per logit) in the workspace and the backward is two fused GEMM kernels);
+    False = nothing of size O(B*T*U*V) survives the forward call; the backward re-runs the projection chunk by chunk
+    (one more tensor-core pass)."""
     return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact,
                             keep_activations)
 
@@ -134,6 +131,34 @@ def joint_logits(enc_acts, pred_acts, W, b):
         st = L.rnntb200_joint_logits(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(out), _ptr(ws))
     _lib.check(st, "rnntb200_joint_logits")
     return out
+
+
+def joint_step(f, g, K1, b1, K2, b2, want_logits=True, want_best=False):
+    """``rnntb200_joint_step``: logits (B,V) of ONE lattice cell per batch row, tanh((f+g) @ K1 + b1) @ K2 + b2, and/or
+    its argmax + log-softmax value.  ``f``, ``g``: (B,P) float32 CUDA views whose last dimension is contiguous (row
+    strides are passed through, so ``encoded[:, i, :]`` / ``pred_out[:, -1, :]`` are not copied).  Not differentiable
+    (inference).  Returns (logits | None, best | None, best_logp | None)."""
+    L = _lib.load()
+    for t, n in ((f, "f"), (g, "g"), (K2, "K2")):
+        if not t.is_cuda or t.dtype != torch.float32:
+            raise TypeError("%s must be a float32 CUDA tensor (rnnt_b200 has no CPU path)" % n)
+    if f.dim() != 2 or g.shape != f.shape or f.stride(1) != 1 or g.stride(1) != 1:
+        raise ValueError("f and g must be (B,P) with a contiguous last dimension")
+    B, P = f.shape
+    K1c = K1.detach().contiguous() if K1 is not None else None
+    K2c = K2.detach().contiguous()
+    H, V = K2c.shape
+    b1c = b1.detach().contiguous() if b1 is not None else None
+    b2c = b2.detach().contiguous() if b2 is not None else None
+    with torch.cuda.device(f.device):
+        logits = torch.empty(B, V, dtype=torch.float32, device=f.device) if want_logits else None
+        best = torch.empty(B, dtype=torch.int32, device=f.device) if want_best else None
+        logp = torch.empty(B, dtype=torch.float32, device=f.device) if want_best else None
+        st = L.rnntb200_joint_step(_ptr(f.detach()), f.stride(0), _ptr(g.detach()), g.stride(0), _ptr(K1c), _ptr(b1c), _ptr(K2c),
+                                   _ptr(b2c), B, P, H, V, _ptr(logits), _ptr(best), _ptr(logp),
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(st, "rnntb200_joint_step")
+    return logits, best, logp
 
 
 class Joint(torch.nn.Module):
@@ -164,9 +189,17 @@ class Joint(torch.nn.Module):
 
     def step(self, f, g):
         """Greedy-decode joint, utils/decoding.py:6-18: ``joint(model, f, g)`` adds ``f`` (B,T,P) to the LAST
-        prediction-network frame ``g[:, -1, :]`` and returns ``outputs[:, 0, 0, :]`` -- the (B,V) logits of frame 0."""
-        enc_acts, pred_acts = self.hoist(f[:, :1, :], g[:, -1:, :])
-        return joint_logits(enc_acts, pred_acts, self.kernel_2, self.bias_2)[:, 0, 0, :]
+        prediction-network frame ``g[:, -1, :]`` and returns ``outputs[:, 0, 0, :]`` -- the (B,V) logits of frame 0.
+        One launch of the library's decode kernel (both Dense layers fused, fp32)."""
+        return joint_step(f[:, 0, :], g[:, -1, :], self.kernel_1, self.bias_1, self.kernel_2, self.bias_2)[0]
+
+    def greedy_step(self, f, g):
+        """The decode step of utils/decoding.py:69-78 in one launch: ``preds = log_softmax(joint(model, f, g))``,
+        ``predicted_id = argmax(preds)``.  Returns (predicted_id (B,) int32, its log-probability (B,) float32); the
+        (B,V) logits are not written at all."""
+        _, best, logp = joint_step(f[:, 0, :], g[:, -1, :], self.kernel_1, self.bias_1, self.kernel_2, self.bias_2,
+                                   want_logits=False, want_best=True)
+        return best, logp
 
     def loss(self, inp_enc, pred_outputs, labels, input_lengths, label_lengths):
         enc_acts, pred_acts = self.hoist(inp_enc, pred_outputs)

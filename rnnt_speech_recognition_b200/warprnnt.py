@@ -105,8 +105,8 @@ class _RNNTOp(torch.autograd.Function):
         costs = torch.empty(B, dtype=torch.float32, device=acts.device)
         ws = torch.empty(workspace_bytes(T, U, B), dtype=torch.uint8, device=acts.device)
         lab = labels if labels.numel() else torch.zeros(1, dtype=torch.int32, device=acts.device)
-        opt = _lib.RnntOptions(_lib.RNNT_GPU, 0, _stream().value, int(blank), T, U, True)
-        with torch.cuda.device(acts.device):
+        with torch.cuda.device(acts.device):     # the stream must be the current stream OF THE TENSORS' DEVICE
+            opt = _lib.RnntOptions(_lib.RNNT_GPU, 0, _stream().value, int(blank), T, U, True)
             st = L.rnntb200_loss_device(_ptr(acts), _ptr(grads), _ptr(lab), _ptr(label_lens), _ptr(act_lens), None,
                                         V, B, _ptr(costs), _ptr(ws), opt)
         _lib.check(st, "rnntb200_loss_device")

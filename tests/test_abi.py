@@ -82,3 +82,22 @@ def test_struct_layout_matches_reference_header():
     assert C.sizeof(_lib.RnntOptions) == 32            # rnnt.h:43-64 on x86-64
     assert _lib.RnntOptions.stream.offset == 8 and _lib.RnntOptions.blank_label.offset == 16
     assert _lib.RnntOptions.batch_first.offset == 28
+
+
+def test_reference_header_links_against_this_library():
+    """Header-level ABI check: tests/abi_harness/abi_harness.cpp includes the REFERENCE's rnnt.h (never copied here) and
+    is linked against librnnt_b200.so -- what tensorflow_binding/src/warprnnt_op.cc:105-141 and
+    pytorch_binding/src/binding.cpp:84-154 do.  `link` mode resolves every symbol and exercises the host-only entry
+    points; the known-answer run on a GPU is tests/test_gpu_loss_op.py::test_abi_harness_kat."""
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    from rnnt_speech_recognition_b200 import _lib
+    _lib.load()
+    exe = ge.build_abi_harness()
+    if exe is None:
+        pytest.skip("no /root/reference here and no prebuilt harness")
+    r = subprocess.run([exe, "link"], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "link ok" in r.stdout

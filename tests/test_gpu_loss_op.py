@@ -143,3 +143,17 @@ def test_forward_backward_likelihood_agree(L):
     oc, _ = o.rnnt_logits_grad(x.detach().cpu().double().numpy(), lab.cpu().numpy(), il.cpu().numpy(),
                                ll.cpu().numpy(), want_grad=False)
     assert_close(costs.detach().cpu().numpy(), oc, rtol=2e-6, atol=1e-3, what="C2-lattice costs")
+
+
+def test_abi_harness_kat():
+    """The C++ harness built against the reference's own rnnt.h (tests/abi_harness) runs the reference's small_test
+    KAT (tests/test_cpu.cpp:12-71) through compute_rnnt_loss on the GPU: cost 4.495666 and the first gradient row."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "tests", "abi_harness", "_build", "abi_harness")
+    if not os.path.exists(exe):
+        pytest.skip("harness not prebuilt (needs /root/reference at build time)")
+    r = subprocess.run([exe, "run"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "run ok" in r.stdout

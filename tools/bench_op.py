@@ -38,8 +38,13 @@ def run_lib(L, fn_name, x, g, lab, il, ll, ws, costs_host, opt_cls, iters=10):
 
 
 def main():
-    import numpy as np
     shapes = [tuple(int(v) for v in sys.argv[1:5])] if len(sys.argv) >= 5 else [(16, 256, 64, 256), (32, 512, 128, 1024)]
+    for res in run_shapes(shapes):
+        print(json.dumps(res))
+
+
+def run_shapes(shapes):
+    import numpy as np
     L = _lib.load()
     ref_path = os.path.join(ROOT, "oracle", "_ref", "libwarprnnt_gpu.so")
     R = C.CDLL(ref_path) if os.path.exists(ref_path) else None
@@ -72,7 +77,8 @@ def main():
             res["max_rel_cost_diff"] = float(np.abs(c1 - c2).max() / np.abs(c2).max())
             res["speedup"] = ms2 / ms
         out.append(res)
-        print(json.dumps(res))
+        del x, g1, ws
+        torch.cuda.empty_cache()
     return out
 
 

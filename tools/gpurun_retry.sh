@@ -1,0 +1,10 @@
+#!/bin/sh
+# usage: tools/gpurun_retry.sh <logfile> <timeout_s> '<command>'   -- retries while the pod answers busy (exit 3 / transient)
+LOG=$1; TMO=$2; shift 2
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun --timeout "$TMO" -- "$@" > "$LOG" 2>&1
+  rc=$?
+  if ! grep -q "status=transient" "$LOG"; then exit $rc; fi
+  sleep 60
+done
+exit 3

@@ -1,0 +1,22 @@
+"""Runs one synthetic joint_rnnt_loss forward+backward on the tensor-core path and saves costs + gradients to an .npz.
+Used by tests that compare two PROCESS-level configurations of the library (environment switches are read once per
+process), e.g. the multi-chunk backward (RNNTB200_CHUNK_MB) against the single-chunk one.
+
+    python tools/joint_dump.py OUT.npz B T U V H seed ragged keep
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+if __name__ == "__main__":
+    from test_gpu_joint import run_joint, synth
+    out = sys.argv[1]
+    B, T, U, V, H, seed, ragged, keep = (int(x) for x in sys.argv[2:10])
+    k = synth(B, T, U, V, H, seed, bool(ragged))
+    costs, grads = run_joint(k, "bf16", keep=bool(keep))
+    np.savez(out, costs=costs, d_enc=grads[0], d_pred=grads[1], dW=grads[2], db=grads[3])
