@@ -58,11 +58,12 @@ inline int tc_num_sms() {
 
 // Geometry of the two backward kernels (bwd_tc.cuh), a pure function of (H, V) and the SM count.
 //   dZ: NP passes over H of NCZ columns; accumulators of two consecutive passes share `sh` TMEM columns.
-//   dW: output tiles of (1 or 2 blocks of 128 rows of H) x 256 columns of V, split over the lattice rows.
+//   dW: output tiles of (2 block slots of 128 rows out of [H blocks..., ONES]) x 256 columns of V, split S ways over the
+//       lattice rows.
 struct BwdGeom {
     int NP, NCZ, priv, sh, odd_base;
     size_t dz_smem, dw_smem;
-    int nVT, nD, nS, S_d, S_s, S_max, dw_grid;
+    int nVT, nHB, nItems, S_max, dw_grid;     // S_max = the split count S
     bool ok;
 };
 inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
@@ -74,17 +75,14 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
     g.sh = 2 * g.NCZ > 512 ? 2 * g.NCZ - 512 : 0;
     g.priv = g.NCZ - g.sh;
     g.odd_base = 512 - g.priv;
-    g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
-    g.dw_smem = 1024 + (size_t)3 * 65536 + (size_t)2 * (64 * 8 + 3 * 64) * 4 + 4 * 256 * 4 + 512;
-    const int nHB = (H + 127) / 128;
-    g.nD = nHB / 2; g.nS = nHB % 2;
+    g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128 + 4096) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+    g.dw_smem = 1024 + (size_t)3 * (65536 + 4096) + 16384 + (size_t)(64 * 8 + 3 * 64) * 4 + 512;
+    g.nHB = (H + 127) / 128;
+    g.nItems = (g.nHB + 2) / 2;               // blocks [0 .. nHB-1, ONES] in pairs
     g.nVT = (V + 255) / 256;
-    const int units = g.nVT * (2 * g.nD + g.nS);
-    g.S_d = 2 * sms / units; if (g.S_d < 1) g.S_d = 1;
-    g.S_s = g.S_d / 2; if (g.S_s < 1) g.S_s = 1;
-    g.S_max = g.S_d > g.S_s ? g.S_d : g.S_s;
-    if (!g.nD) g.S_max = g.S_s;
-    g.dw_grid = g.nVT * (g.nD * g.S_d + g.nS * g.S_s);
+    g.S_max = sms / (g.nVT * g.nItems);
+    if (g.S_max < 1) g.S_max = 1;
+    g.dw_grid = g.nVT * g.nItems * g.S_max;
     g.ok = g.dz_smem <= 232448 && g.dw_smem <= 232448;
     return g;
 }
@@ -118,7 +116,7 @@ __device__ __forceinline__ TileInfo decode_tile(const JointTcParams& p, int tile
     return ti;
 }
 
-// W (H,V) fp32 -> Wt (V,H) fp16 [B operand of the logits GEMM, K=h] and Wb (H,V) bf16 [B operand of dZ, K=v]
+// W (H,V) fp32 -> Wt (V,H) fp16 [B operand of the logits GEMM, K=h] and Wb (H,V) fp16 [B operand of dZ, K=v]
 __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt,
                                                         __nv_bfloat16* __restrict__ Wb, int H, int V) {
     __shared__ float tile[32][33];
@@ -128,7 +126,7 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
         const int h = h0 + i, v = v0 + tx;
         const float w = (h < H && v < V) ? W[(size_t)h * V + v] : 0.f;
         tile[i][tx] = w;
-        if (h < H && v < V) Wb[(size_t)h * V + v] = __float2bfloat16(w);
+        if (h < H && v < V) reinterpret_cast<__half*>(Wb)[(size_t)h * V + v] = __float2half_rn(w);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -254,7 +252,7 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 // Workspace of the tensor-core path (a pure function of the descriptor).  The kept arrays (numerators + maxima) are
 // laid out per 128-row tile; the batch is processed in utterance chunks that keep them under ~16 GiB.
 struct TcScratch {
-    __nv_bfloat16 *Wt, *Wb;                 // W^T (V,H) fp16 [forward B operand] and W (H,V) bf16 [dZ B operand]
+    __nv_bfloat16 *Wt, *Wb;                 // W^T (V,H) fp16 [forward B operand] and W (H,V) fp16 [dZ B operand] (16-bit storage)
     __nv_bfloat16* dl;                      // (rows_chunk, V) fp16 softmax numerators 2^(y - m)
     float* gm;                              // (row blocks, V/32, 128) fp32 running maxima m (log2 domain)
     int* slot;                              // tile -> compact row block (-1: outside the valid lattice), per chunk
@@ -263,6 +261,8 @@ struct TcScratch {
     float* ppl;                             // (nTb, bchunk, maxU, H) fp32 partial planes of d_pred (bwd_dz_kernel)
     float* dWp;                             // (S_max, H, V) fp32 split-K planes of dW (bwd_dw_kernel)
     float* dbp;                             // (S_max, V) planes of db
+    float4* rowcoef;                        // (rows_chunk) per-row backward coefficients (row_coef_kernel)
+    int* rowlab;                            // (rows_chunk) label column of the row or -1
     int bchunk;                             // utterances per chunk
     size_t rows_chunk;                      // bchunk * tiles_per_utt * 128
     size_t bytes;
@@ -297,6 +297,8 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.ppl = reinterpret_cast<float*>(take((size_t)g.nTb * bc * d.maxU * d.H * 4));
     s.dWp = reinterpret_cast<float*>(take((size_t)bg.S_max * d.H * d.V * 4));
     s.dbp = reinterpret_cast<float*>(take((size_t)bg.S_max * d.V * 4));
+    s.rowcoef = reinterpret_cast<float4*>(take(s.rows_chunk * 16));
+    s.rowlab = reinterpret_cast<int*>(take(s.rows_chunk * 4));
     s.bytes = (size_t)(p - static_cast<char*>(base));
     return s;
 }
@@ -348,6 +350,20 @@ inline bool tc_smem_optin(const void* func) {
 #include "bwd_tc.cuh"
 
 namespace rb {
+
+// RNNTB200_PROF=1 (bring-up): the backward kernels record per-role wait cycles into a managed buffer that
+// rnntb200_debug_prof() exposes (tools/role_profile.py); off by default, never touched otherwise.
+inline long long* tc_prof_buffer(int which) {
+    static long long* buf[2] = {nullptr, nullptr};
+    static int on = -1;
+    if (on < 0) { const char* e = getenv("RNNTB200_PROF"); on = e ? atoi(e) : 0; }
+    if (!on) return nullptr;
+    if (!buf[which]) {
+        if (cudaMallocManaged(reinterpret_cast<void**>(&buf[which]), sizeof(long long) * 256 * 4 * 8) != cudaSuccess) return nullptr;
+        cudaMemset(buf[which], 0, sizeof(long long) * 256 * 4 * 8);
+    }
+    return buf[which];
+}
 
 inline bool tc_supported(const rnntb200JointDesc& d) {
     return tc_geometry(d.maxT, d.maxU, d.H, d.V).ok && tc3_geometry(d.H, d.V).ok && bwd_geometry(d.H, d.V).ok;
@@ -410,14 +426,16 @@ inline rnntStatus_t tc_forward(const rnntb200JointDesc& d, void* scratch, const 
     return tc_run_forward<false>(d, g, sc, enc, pred, bias, labels, ylen, xlen, lse, lpb, lpl, 0, d.B, s, launches);
 }
 
+struct LossPlanes { const float *lse, *lpb, *lpl, *alphas, *betas, *llf; };   // outputs of the forward + alpha/beta (loss workspace)
+
 // Backward with the library's own tcgen05 kernels (bwd_tc.cuh).  Per utterance chunk: (a keeping
 // forward of the chunk unless the forward call already kept the whole batch) -> bwd_dz_kernel -> d_pred plane sum ->
 // bwd_dw_kernel; after the last chunk the split-K planes of dW / db are summed.  Stream-ordered, no host
 // synchronisation, no library calls.
 inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                 const float* bias, const int* labels, const int* ylen, const int* xlen,
-                                const float4* coef, float* d_enc, float* d_pred, float* dW, float* db,
-                                cudaStream_t s, unsigned* launches) {
+                                const LossPlanes& lp, const float* grad_costs, float* gscale, float* d_enc, float* d_pred,
+                                float* dW, float* db, cudaStream_t s, unsigned* launches) {
     if (!tc_supported(d)) return tc_unsupported(d);
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     const BwdGeom bg = bwd_geometry(d.H, d.V);
@@ -425,6 +443,8 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     const bool kept = tc_keep(d, sc);
     if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel)))
         return RNNT_STATUS_EXECUTION_FAILED;
+    gscale_kernel<<<1, 256, 0, s>>>(grad_costs, d.B, gscale);
+    *launches += 1;
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
         return RNNT_STATUS_MEMOPS_FAILED;
@@ -445,17 +465,27 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         p.enc = enc; p.pred = pred; p.labels = labels; p.xlen = xlen; p.ylen = ylen;
         p.maxT = d.maxT; p.maxU = d.maxU; p.H = d.H; p.V = d.V; p.blank = d.blank_label;
         p.nTb = g.nTb; p.nUb = g.nUb; p.b0 = b0; p.nb = nb;
-        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.coef = coef; p.gm = sc.gm;
+        {   // per-row coefficients of this chunk, in the row order of the kept arrays
+            ScopedTimer tmr("row_coef_kernel", s);
+            row_coef_kernel<<<(unsigned)(((size_t)nb * g.nTb * g.nUb * 128 + 255) / 256), 256, 0, s>>>(
+                sc.tile_of_slot, sc.count, b0, g.nTb, g.nUb, xlen, ylen, labels, d.blank_label, d.maxT, d.maxU,
+                (long long)(d.maxT + d.maxU - 1) * d.maxU, lp.lse, lp.lpb, lp.lpl, lp.alphas, lp.betas, lp.llf, grad_costs, gscale,
+                sc.rowcoef, sc.rowlab);
+            *launches += 1;
+        }
+        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.rowcoef = sc.rowcoef; p.rowlab = sc.rowlab; p.gm = sc.gm;
         p.NP = bg.NP; p.NCZ = bg.NCZ; p.priv = bg.priv; p.sh = bg.sh; p.odd_base = bg.odd_base;
         p.d_enc = d_enc; p.ppred = sc.ppl;
-        p.nVT = bg.nVT; p.nD = bg.nD; p.nS = bg.nS; p.S_d = bg.S_d; p.S_s = bg.S_s; p.Hrows = d.H;
-        p.dWp = sc.dWp; p.dbp = sc.dbp; p.accumulate = 1;
+        p.nVT = bg.nVT; p.nItems = bg.nItems; p.nHB = bg.nHB; p.S = bg.S_max; p.Hrows = d.H;
+        p.dWp = sc.dWp; p.dbp = sc.dbp; p.gscale = gscale; p.dbg = tc_dbg();
+        long long* prof_dz = tc_prof_buffer(0), *prof_dw = tc_prof_buffer(1);
         // rows of d_enc whose t-block lies outside the utterance are never visited by the dZ kernel
         if (cudaMemsetAsync(d_enc + (size_t)b0 * d.maxT * d.H, 0, sizeof(float) * (size_t)nb * d.maxT * d.H, s) != cudaSuccess)
             return RNNT_STATUS_MEMOPS_FAILED;
         {
             const int nruns = nb * g.nTb;
             ScopedTimer tmr("bwd_dz_kernel", s);
+            p.prof = prof_dz;
             bwd_dz_kernel<<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, p);
         }
         {
@@ -466,6 +496,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         }
         {
             ScopedTimer tmr("bwd_dw_kernel", s);
+            p.prof = prof_dw;
             bwd_dw_kernel<<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
         }
         *launches += 3;

@@ -8,8 +8,9 @@
 // staging pass, no inter-warp barrier, no register prefetch buffers.
 //
 // Operand format: fp16 (same tcgen05.mma.kind::f16 rate as bf16, 11-bit instead of 8-bit significand): z is in
-// [-1, 1] and W ~ 1/sqrt(H), both far inside the fp16 range; tanh is evaluated to fp32 accuracy (ex2 + rcp) so that
-// the operand rounding (2^-12) is the only error of the logits.
+// [-1, 1] and W ~ 1/sqrt(H), both far inside the fp16 range.  tanh is tanh.approx.f32 (2^-11 relative, one MUFU op);
+// the fp32-accurate form (ex2 + rcp, two MUFU ops: +0.45 ms per launch at C3 because z production is exposed once per
+// tile) changed neither the cost error (2.3e-5) nor the gradient error (2.9e-3) at C3 -- profiles/r02/accuracy.json.
 //
 // Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
 //
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         // ===================== producers (warps 4-11): thread = (lattice row r2 = TMEM lane, k-half hh) =====================
         const int pw = warp - 4;
         const int q4 = pw & 3, hh = pw >> 2, r2 = q4 * 32 + lane;
-        const bool fast_tanh = (p.dbg & 512) != 0;
+        const bool fast_tanh = (p.dbg & 512) == 0;
+        const uint32_t insm_a = ptx::smem_u32(insm);
         uint32_t it = 0; int st = 0; uint32_t ph = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
@@ -224,18 +226,18 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
             for (int kb = 0; kb < KB; ++kb) {
                 ptx::mbar_wait(&in_full[st], ph);
-                const uint8_t* base = insm + (size_t)st * IN_STAGE;
-                const uint8_t* prow = base + (size_t)hh * 16384 + ul * 128;          // SW128: chunk c at (c ^ (row & 7)) * 16
-                const uint8_t* erow = base + 32768 + tl * 256 + hh * 128;            // plain layout
+                const uint32_t base = insm_a + (uint32_t)st * IN_STAGE;
+                const uint32_t prow = base + (uint32_t)(hh * 16384 + ul * 128);      // SW128: chunk c at (c ^ (row & 7)) * 16
+                const uint32_t erow = base + 32768u + (uint32_t)(tl * 256 + hh * 128);   // plain layout
                 uint32_t zr[16];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
-                    const float4 q = *reinterpret_cast<const float4*>(prow + ((c ^ (ul & 7)) << 4));
-                    const float4 e = *reinterpret_cast<const float4*>(erow + (c << 4));
+                    const float4 q = ptx::lds128f(prow + (uint32_t)((c ^ (ul & 7)) << 4));
+                    const float4 e = ptx::lds128f(erow + (uint32_t)(c << 4));
                     if (ok && !fast_tanh) {
                         zr[c * 2 + 0] = ptx::pack_f16x2(ptx::tanh_accurate(e.x + q.x), ptx::tanh_accurate(e.y + q.y));
                         zr[c * 2 + 1] = ptx::pack_f16x2(ptx::tanh_accurate(e.z + q.z), ptx::tanh_accurate(e.w + q.w));
-                    } else if (ok) {   // RNNTB200_DBG bit 512: tanh.approx (one MUFU op instead of two, 2^-11 relative) -- A/B switch
+                    } else if (ok) {   // default: tanh.approx (one MUFU op instead of two, 2^-11 relative); RNNTB200_DBG bit 512 selects the accurate form
                         zr[c * 2 + 0] = ptx::pack_f16x2(ptx::tanh_approx(e.x + q.x), ptx::tanh_approx(e.y + q.y));
                         zr[c * 2 + 1] = ptx::pack_f16x2(ptx::tanh_approx(e.z + q.z), ptx::tanh_approx(e.w + q.w));
                     } else {
@@ -257,6 +259,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     } else if (warp < 4) {
         // ===================== epilogue warps 0-3: thread = lattice cell (TMEM lane) =====================
         constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+        const uint32_t bias_a = ptx::smem_u32(bias2);
         uint32_t g = 0;
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
@@ -281,7 +284,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                     ptx::tmem_ld_wait();
                     if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
                     const int col0 = c * NC + j * 32;
-                    const float bv = bias_in_smem ? bias2[col0 + lane] : __ldg(p.bias + col0 + lane) * LOG2E;
+                    const float bv = bias_in_smem ? __uint_as_float(ptx::lds32(bias_a + (uint32_t)((col0 + lane) * 4)))
+                                                  : __ldg(p.bias + col0 + lane) * LOG2E;
                     float y[32];
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
@@ -294,7 +298,8 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                         float acc = 0.f;
                         if (MODE == 0) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i) acc += ptx::ex2_approx(y[i] - mn);
+                            for (int i = 0; i < 32; i += 2)   // (same order of additions as MODE 2: the two modes return identical bits)
+                                acc += ptx::ex2_approx(y[i] - mn) + ptx::ex2_approx(y[i + 1] - mn);
                         } else {
                             // keep the numerators: 2^(y - mn) in (0, 1] as fp16 (2^-11 relative), with mn beside them
                             uint32_t o[16];

@@ -151,7 +151,7 @@ rnntStatus_t compute_impl(const T* acts, T* grads, const int* labels, const int*
 // ------------------------------------------------------------------------------------------
 struct JointWs {
     LossWs<float> loss;
-    float4* coef;      // (N) per-cell backward coefficients (TC path)
+    float* gscale;     // {S, 1/S}: power-of-two scale of the fp16 logit gradients (TC path)
     char* scratch;     // path-specific
     size_t scratch_bytes;
     long long chunk_rows;  // exact path
@@ -159,8 +159,8 @@ struct JointWs {
     JointWs(const rnntb200JointDesc& d, void* base) : loss(base, d.B, d.maxT, d.maxU) {
         const size_t N = (size_t)d.B * d.maxT * d.maxU;
         size_t off = align_up(loss.bytes, 256);
-        coef = reinterpret_cast<float4*>(static_cast<char*>(base) + off);
-        off += align_up(N * sizeof(float4), 256);
+        gscale = reinterpret_cast<float*>(static_cast<char*>(base) + off);
+        off += 256;
         scratch = static_cast<char*>(base) + off;
         if (d.precision == RNNTB200_FP32_EXACT) {
             const size_t per_row = (size_t)(2 * d.H + d.V) * sizeof(float);
@@ -404,17 +404,10 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
         return exact_backward(d, ws, enc, pred, W, bias, labels, label_lengths, input_lengths, grad_costs, d_enc,
                               d_pred, dW, db, s);
 #ifndef RNNTB200_NO_TC
-    const long long N = (long long)d.B * d.maxT * d.maxU;
-    rb::ScopedTimer* tmc = new rb::ScopedTimer("cell_coef_kernel", s);
-    rb::cell_coef_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(
-        N, input_lengths, label_lengths, labels, d.blank_label, d.maxT, d.maxU, skew_plane(d.maxT, d.maxU), ws.loss.lse, ws.loss.lpb,
-        ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf, grad_costs, ws.coef);
-    delete tmc;
-    RB_LAUNCHED(1);
-    if (check_launch()) return RNNT_STATUS_EXECUTION_FAILED;
     unsigned nl = 0;
-    rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, bias, labels, label_lengths, input_lengths, ws.coef, d_enc,
-                                      d_pred, dW, db, s, &nl);
+    const rb::LossPlanes lp{ws.loss.lse, ws.loss.lpb, ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf};
+    rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, bias, labels, label_lengths, input_lengths, lp, grad_costs,
+                                      ws.gscale, d_enc, d_pred, dW, db, s, &nl);
     RB_LAUNCHED(nl);
     return st;
 #else
@@ -458,6 +451,11 @@ rnntStatus_t rnntb200_joint_step(const float* f, long long ldf, const float* g, 
     RB_LAUNCHED(1);
     return check_launch();
 }
+
+#ifndef RNNTB200_NO_TC
+// bring-up only (not in the public header): role wait-cycle counters of the last backward launch, see tc_prof_buffer()
+const long long* rnntb200_debug_prof(int which) { return rb::tc_prof_buffer(which); }
+#endif
 
 unsigned long long rnntb200_launch_count() { return g_launches.load(); }
 

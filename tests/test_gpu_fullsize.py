@@ -38,16 +38,16 @@ def test_c3_bf16_vs_fp32_exact(c3):
     k, c16, g16 = c3
     c32, g32 = run_joint(k, "fp32")
     assert np.all(np.isfinite(c16))
-    assert_close(c16, c32, rtol=2e-3, atol=1e-2, what="costs")
+    assert_close(c16, c32, rtol=2e-4, atol=1e-2, what="costs")          # measured 2.4e-5 (profiles/r02/accuracy.json)
     for a, b, n in zip(g16, g32, NAMES):
         assert np.all(np.isfinite(a)), n
         rel = np.linalg.norm(a - b) / np.linalg.norm(b)
-        assert rel < 4e-2, (n, rel)          # measured 1.4e-2 .. 2.6e-2 (profiles/r01/accuracy_c3.json): bf16 operand rounding
-    # kept-activation backward against the recomputing backward at full size
+        assert rel < 5e-3, (n, rel)          # measured <= 3e-3 (profiles/r02/accuracy.json); round 1 (bf16 operands): 2.6e-2
+    # kept-activation backward against the recomputing backward at full size: the same kernels on the same numerators
     c_re, g_re = run_joint(k, "bf16", keep=False)
-    assert_close(c16, c_re, rtol=1e-6, atol=1e-3, what="costs keep/recompute")
+    assert np.array_equal(c16, c_re)
     for a, b, n in zip(g16, g_re, NAMES):
-        assert np.linalg.norm(a - b) <= 2e-3 * np.linalg.norm(b), n
+        assert np.array_equal(a, b), n
 
 
 def test_c3_softmax_shift_invariance(c3):
@@ -72,23 +72,25 @@ def test_c3_batch_additivity_and_permutation(c3):
         assert_close(gh[0], grads[0][idx], rtol=1e-4, atol=0, ntol=1e-4, what="d_enc of a sub-batch")
         assert_close(gh[1], grads[1][idx], rtol=1e-4, atol=0, ntol=1e-4, what="d_pred of a sub-batch")
         dW_sum, db_sum = dW_sum + gh[2].astype(np.float64), db_sum + gh[3].astype(np.float64)
-    assert_close(dW_sum, grads[2], rtol=0, atol=0, ntol=1e-4, what="dW additivity")
-    assert_close(db_sum, grads[3], rtol=0, atol=0, ntol=1e-4, what="db additivity")
+    # (split-K ranges differ between the full batch and its halves: fp32 tensor-core accumulation order, ~1e-4 relative on
+    #  the largest entries -- db[blank] is a same-sign sum over 2 M rows)
+    assert_close(dW_sum, grads[2], rtol=0, atol=0, ntol=5e-4, what="dW additivity")
+    assert_close(db_sum, grads[3], rtol=0, atol=0, ntol=5e-4, what="db additivity")
     perm = np.random.default_rng(7).permutation(B)
     cp, gp = run_joint(sub(k, perm), "bf16")
     assert_close(cp, costs[perm], rtol=1e-6, atol=1e-3, what="permuted costs")
-    assert_close(gp[2], grads[2], rtol=0, atol=0, ntol=1e-4, what="dW under permutation")
+    assert_close(gp[2], grads[2], rtol=0, atol=0, ntol=5e-4, what="dW under permutation")
 
 
 def test_c3_ragged_matches_fp32_exact():
-    """Same shape, ragged lengths (compacted tiles + partially filled tiles at full width)."""
+    """Same shape, ragged lengths (device-ranked tiles + partially filled tiles at full width)."""
     k = synth(8, C3["T"], C3["U"], C3["V"], C3["H"], 2027, ragged=True)
     c32, g32 = run_joint(k, "fp32")
     for keep in (True, False):
         c16, g16 = run_joint(k, "bf16", keep=keep)
-        assert_close(c16, c32, rtol=2e-3, atol=1e-2, what="costs")
+        assert_close(c16, c32, rtol=2e-4, atol=1e-2, what="costs")
         for a, b, n in zip(g16, g32, NAMES):
             rel = np.linalg.norm(a - b) / np.linalg.norm(b)
-            assert rel < 4e-2, (n, rel, keep)
+            assert rel < 5e-3, (n, rel, keep)
         for b in range(8):
             assert not g16[0][b, k["input_lengths"][b]:].any() and not g16[1][b, k["label_lengths"][b] + 1:].any()

@@ -34,7 +34,32 @@ def main(path):
             n += 1
         res[key] = d
     print(json.dumps(res, indent=1))
+    return res
+
+
+def traffic(res, steps):
+    """profiles/rNN/traffic.json for bench.py: DRAM bytes per launch of each kernel (mean over its launches in the
+    capture) and per step, tagged with the hash of the CUDA sources the capture was taken from."""
+    import os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    per, cnt = {}, {}
+    for key, d in res.items():
+        name = key.split(" #")[0]
+        short = name.split("(")[0].replace("rb::", "").replace("void ", "").strip()
+        def num(k):
+            v = d.get(k, "0").split()
+            x = float(v[0].replace(",", "")) if v else 0.0
+            u = v[1].lower() if len(v) > 1 else "byte"
+            return x * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(u, 1)
+        b = num("dram__bytes_read.sum") + num("dram__bytes_write.sum")
+        per[short] = per.get(short, 0.0) + b
+        cnt[short] = cnt.get(short, 0) + 1
+    return {"csrc_sha16": bench.csrc_sha16(), "kernels": {k: per[k] / cnt[k] for k in per},
+            "step": sum(per.values()) / max(steps, 1), "launches_in_capture": cnt, "steps_in_capture": steps}
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    r = main(sys.argv[1])
+    if len(sys.argv) >= 4:      # ncu_summary.py X.ncu-rep <steps captured> traffic.json
+        json.dump(traffic(r, int(sys.argv[2])), open(sys.argv[3], "w"), indent=1)

@@ -7,11 +7,11 @@
 //           every CTA dumps its 128 x 64 accumulator; tools/mma2_probe.py compares with the exact integer GEMM
 //   mode 1  cycles per cta_group::2 MMA when one elected lane of the LEADER issues 20 per block (the fused kernel's
 //           issue pattern), A walking over 320 columns, B over 5 K-block slabs
-// Status: compiles for sm_100a; NOT yet run on hardware (written after the round's GPU budget was spent).
-// Outside the library build: tools/build_wip.sh compiles it into csrc/wip/libwip.so (export rnntb200_wip_mma2_probe)
-// for tools/mma2_probe.py.
+// Status: run on B200 in round 2 (profiles/r02/mma2_probe.log): every accumulator entry exact for 1 and 74 pairs,
+// 32.1 cycles per cta_group::2 MMA (the dispatch floor).  Outside the library build: tools/probes/build_probe.sh
+// compiles it into tools/probes/libprobe.so (export rnntb200_wip_mma2_probe) for tools/probes/mma2_probe.py.
 #pragma once
-#include "../ptx.cuh"
+#include "ptx.cuh"
 
 namespace rb {
 namespace c2 {

@@ -1,4 +1,4 @@
-"""Bring-up probe of the 2-CTA MMA form (csrc/wip/mma2_probe.cuh, built by tools/build_wip.sh into csrc/wip/libwip.so): `timeout 60 python tools/mma2_probe.py`.
+"""Bring-up probe of the 2-CTA MMA form (tools/probes/mma2_probe.cuh, built by tools/probes/build_probe.sh into tools/probes/libprobe.so): `timeout 60 python tools/probes/mma2_probe.py`.
 
 mode 0: every CTA of every pair dumps its 128 x 64 accumulator of D = A_cta . B^T with small-integer operands generated
         in the kernel; compared EXACTLY with the integer GEMM below.  A mismatch pattern tells which assumption of the
@@ -13,11 +13,11 @@ import sys
 import numpy as np
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SO = os.path.join(ROOT, "rnnt_speech_recognition_b200", "csrc", "wip", "libwip.so")
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "libprobe.so")
 if not os.path.exists(SO):
     import subprocess
-    subprocess.run([os.path.join(ROOT, "tools", "build_wip.sh")], check=True)
+    subprocess.run([os.path.join(HERE, "build_probe.sh")], check=True)
 L = C.CDLL(SO)
 KB, N = 5, 64
 K = KB * 64
