@@ -1,49 +1,48 @@
 // bwd_tc.cuh -- the two backward contractions of the joint (TF autograd through model.py:162-166,
-// triggered at run_rnnt.py:284) as hand-written tcgen05 kernels that consume what the forward KEPT (fp16 softmax
-// numerators e = 2^(y - m) and the running maxima m per 32-column group) and fuse their neighbours away:
+// triggered at run_rnnt.py:284) as hand-written tcgen05 kernels.  They consume what the forward KEPT: the bf16 softmax
+// numerators E[row, v] = 2^(y_v - ref_row) (one reference per lattice row) -- the logit gradient of a row is
+//     dl[row, :] = rs_row * E'[row, :],     rs_row = g_b * 2^(ref_row + (alpha + beta - ll - lse) * log2 e)
+// where E' is E with the row's two special columns (blank, label) replaced by (final value) / rs_row (row_scale_kernel,
+// two 2-byte writes per row).  A scale per ROW commutes with both GEMMs, so neither needs a per-element prologue:
 //
-//   bwd_dz_kernel   dZ[rows,H] = dl[rows,V] . W^T   with  dl = e * g*2^(m + kd)  formed in shared memory by a SIMT
-//                   prologue on the TMA-loaded A stage (4 HMUL2 per 8 numerators; the two special columns patched
-//                   from row_coef_kernel's values), and an epilogue that applies (1 - tanh^2(enc+pred)), sums the tile over u (-> d_enc,
-//                   accumulated in REGISTERS along a run of tiles and stored once) and over t (-> one fp32 partial
-//                   plane of d_pred per t-block).  Neither dl nor dZ ever exists in HBM.
-//   bwd_dw_kernel   dW[H,V] (+)= z^T . dl   as a split-K GEMM over the lattice rows: the A operand z^T is REGENERATED
-//                   from enc/pred by producer warps (K-major SWIZZLE_128B tiles), the B operand is the kept
-//                   numerators loaded MN-major by TMA and scaled in place; db = sum_rows dl is one more row of
-//                   the product (an A block whose row 0 is all ones).  Partial tiles go to fp32 planes
-//                   (deterministic), summed by sum_planes_kernel.
+//   bwd_dz_kernel   dZ[rows,H] = rs_row * (E'[rows,V] . W^T): both operands straight from TMA (K-major), the row scale,
+//                   (1 - tanh^2(enc+pred)) and the tile's sums over u (-> d_enc, accumulated in REGISTERS along a run of
+//                   tiles and stored once) and over t (-> one fp32 partial plane of d_pred per t-block) in the epilogue.
+//                   Neither dl nor dZ ever exists in HBM.
+//   bwd_dw_kernel   dW[H,V] (+)= (rs_row * z)^T . E'  as a split-K GEMM over the lattice rows: the A operand is REGENERATED
+//                   from enc/pred by producer warps (tanh, times the row scale, K-major SWIZZLE_128B tiles), the B operand
+//                   is E' loaded MN-major by TMA; db = sum_rows dl is one more row of the product (an A block whose row 0
+//                   holds the row scales).  Partial tiles go to fp32 planes (deterministic), summed by sum_planes_kernel.
 //
-// Number format: every operand of the two GEMMs is fp16 (11-bit significand; same tcgen05.mma.kind::f16 rate as bf16).
-// The logit gradients are bounded by the upstream gradient g = d(total)/d(cost_b), so row_coef_kernel pre-multiplies
-// them by a power of two S chosen from max_b |g_b| (gscale_kernel: 128 < S*max|g| <= 256), which puts them in the
-// middle of the fp16 range whatever the caller's loss scaling is; the epilogues multiply by 1/S (exact).
+// All operands bf16 (E' needs the exponent range: it is relative to a reference that may lie far below the row maximum),
+// fp32 accumulation.  Tile geometry: 16 x 8 lattice tiles (TT = 16 time steps, UU = 8 label positions), row r = tl*8 + ul of
+// a tile is TMEM lane r; rows of tile `tile` live at row block slot[tile] of the kept arrays.
 //
-// Tile geometry: 16 x 8 lattice tiles (TT = 16 time steps, UU = 8 label positions), row r = tl*8 + ul of a tile is
-// TMEM lane r; rows of tile `tile` live at row block slot[tile] of the kept arrays.
+// What round 2 measured on the way here (profiles/r02/README.md): a first version scaled the numerators per 32-column
+// group inside shared-memory prologues (fp16 -> fp32 -> bf16, later four HMUL2 per 16 bytes); the role wait counters
+// (RNNTB200_PROF) showed both MMA warps waiting on those prologue warps 60-85 % of the time (dW 15 -> 5.5 ms, dZ 4.6 -> 4.1 ms
+// after three rounds of tuning) -- the per-row reference removed the prologues altogether.
 #pragma once
 #include "joint_tc.cuh"
 
 namespace rb {
 
 constexpr int BW_TT = 16, BW_UU = 8;
-constexpr int DZ_THREADS = 448;      // warp 0 TMA | 1 MMA | 2-5 A-stage scalers | 6-13 epilogue
+constexpr int DZ_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 epilogue
 constexpr int DZ_STAGES = 3;
-constexpr int DW_THREADS = 448;      // warp 0 TMA | 1 MMA | 2-5 B-stage scalers | 6-13 z producers, then epilogue
+constexpr int DW_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 z producers, then epilogue
 constexpr int DW_STAGES = 3;
 constexpr int DW_NV = 256;           // vocabulary columns per dW output tile
 
 struct BwdParams {
     const float* enc; const float* pred;
-    const int* labels; const int* xlen; const int* ylen;
-    int maxT, maxU, H, V, blank;
+    const int* xlen; const int* ylen;
+    int maxT, maxU, H, V;
     int nTb, nUb, b0, nb;
     const int* slot;            // tile -> row block of the kept arrays (-1: tile outside the valid lattice)
     const int* tile_of_slot;    // inverse map (valid tiles only)
     const int* count;           // number of valid tiles (device word)
-    const float4* rowcoef;      // per row of the kept arrays (kd2, S*g, S*dl_blank, S*dl_label)   [row_coef_kernel]
-    const int* rowlab;          // per row: label column or -1
-    const float* gscale;        // {S, 1/S}
-    const float* gm;            // [row block][V/32][128] running maxima of the kept numerators (log2 domain)
+    const float* rowscale;      // per row of the kept arrays: rs_row (0 for rows outside the lattice)   [row_scale_kernel]
     // ---- dZ kernel
     int NP, NCZ, priv, sh, odd_base;   // passes over H, columns per pass, private / shared accumulator columns
     float* d_enc;               // (B, maxT, H), rows of this launch's utterances are fully written
@@ -53,25 +52,11 @@ struct BwdParams {
     float* dWp;                 // (S, Hrows, V) partial planes of dW (zeroed by the host, accumulated over utterance chunks)
     float* dbp;                 // (S, V) partial planes of db
     long long* prof;            // optional (RNNTB200_PROF=1): per-CTA cycle counters of the roles' waits
-    int dbg;                    // RNNTB200_DBG bring-up switches (results are wrong by design): 1024 no proxy fence in the prologues, 2048 no prologue work
 };
 
-// ---------------------------------------------------------------------------------------------------------------
-// shared helpers
-// ---------------------------------------------------------------------------------------------------------------
-// 8 kept numerators (fp16) * scale -> 8 fp16: four HMUL2, nothing else.  (The two special columns of a row are patched
-// AFTER the bulk store with predicated 2-byte stores by the thread that wrote their chunk: folding the patch into this
-// function cost ~60 if-converted instructions per chunk and made the prologues the bottleneck of both kernels.)
-__device__ __forceinline__ uint4 scale_chunk(const uint4 x, __half2 s2) {
-    uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const __half2 h = __hmul2(*reinterpret_cast<const __half2*>(&w[i]), s2);
-        w[i] = *reinterpret_cast<const uint32_t*>(&h);
-    }
-    return make_uint4(w[0], w[1], w[2], w[3]);
-}
-__device__ __forceinline__ uint16_t f16_bits(float v) { return __half_as_ushort(__float2half_rn(v)); }
+// cycle accounting for bring-up (p.prof != NULL): t += clock64() spent in the bracketed region, by one lane of one warp per role
+#define RB_PROF_BEGIN(flag) const long long _t0 = (flag) ? clock64() : 0
+#define RB_PROF_END(flag, acc) if (flag) (acc) += clock64() - _t0
 
 // ---------------------------------------------------------------------------------------------------------------
 // dZ kernel
@@ -80,27 +65,19 @@ __device__ __forceinline__ uint16_t f16_bits(float v) { return __half_as_ushort(
 // valid tiles along u; inside a tile NP passes over H.  Accumulators: an even unit uses TMEM columns [0, NCZ), an odd
 // unit [priv .. NCZ) (the SHARED zone, drained first by the epilogue) + [odd_base, 512): two units are in flight
 // (MMA of unit q+1 over the epilogue of unit q) although 2*NCZ may exceed the 512 columns.
-// cycle accounting for bring-up (p.prof != NULL): t += clock64() spent in the bracketed region, by one lane of one warp per role
-#define RB_PROF_BEGIN(flag) const long long _t0 = (flag) ? clock64() : 0
-#define RB_PROF_END(flag, acc) if (flag) (acc) += clock64() - _t0
-
 __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_constant__ CUtensorMap tmap_e,
                                                                const __grid_constant__ CUtensorMap tmap_wp,
                                                                const __grid_constant__ CUtensorMap tmap_ws,
                                                                const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NCZ = p.NCZ, NP = p.NP, priv = p.priv, sh = p.sh, KBV = p.V >> 6, G = p.V >> 5;
-    // stage = A [128 x 64] (16 KB) | B [NCZ x 64] | meta: gm of the stage's two column groups (2 x 128 floats); in the first
-    // stage of a unit also the tile's per-row coefficients (128 x float4) and label columns (128 x int)
-    const uint32_t meta_off = 16384u + (uint32_t)NCZ * 128u, stage_bytes = meta_off + 4096u;
-    const uint32_t tx_ab = 16384u + (uint32_t)NCZ * 128u;
+    const int NCZ = p.NCZ, NP = p.NP, priv = p.priv, sh = p.sh, KBV = p.V >> 6;
+    const uint32_t stage_bytes = 16384u + (uint32_t)NCZ * 128u;            // A [128 rows x 64 v] | B [NCZ h x 64 v]
     uint8_t* dpb = smem + (size_t)DZ_STAGES * stage_bytes;                 // [hh][buf][4][8][36] floats
     constexpr int DP_ONE = 4 * 8 * 36;                                     // floats per (hh, buf)
     uint64_t* bars = reinterpret_cast<uint64_t*>(dpb + 2 * 2 * DP_ONE * 4);
-    uint64_t* stage_full = bars;                     // [DZ_STAGES] TMA -> scalers, MMA
-    uint64_t* a_ready = stage_full + DZ_STAGES;      // [DZ_STAGES] scalers -> MMA
-    uint64_t* stage_empty = a_ready + DZ_STAGES;     // [DZ_STAGES] MMA -> TMA
+    uint64_t* stage_full = bars;                     // [DZ_STAGES] TMA -> MMA
+    uint64_t* stage_empty = stage_full + DZ_STAGES;  // [DZ_STAGES] MMA -> TMA
     uint64_t* acc_full = stage_empty + DZ_STAGES;    // [2] MMA -> epilogue (unit parity)
     uint64_t* priv_free = acc_full + 2;              // [2] epilogue -> MMA
     uint64_t* shared_free = priv_free + 2;           // [1]
@@ -108,7 +85,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DZ_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&a_ready[i], 4); ptx::mbar_init(&stage_empty[i], 1); }
+        for (int i = 0; i < DZ_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&stage_empty[i], 1); }
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], 8); }
         ptx::mbar_init(shared_free, 8);
         ptx::fence_barrier_init();
@@ -120,7 +97,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int nruns = p.nb * p.nTb;
-    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);
     long long pc[4] = {0, 0, 0, 0};
     const long long t_start = pf ? clock64() : 0;
 
@@ -140,13 +117,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                         const int n0 = pass * NCZ;
                         for (int kb = 0; kb < KBV; ++kb) {
                             { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
-                            ptx::mbar_arrive_expect_tx(&stage_full[stage], tx_ab + 1024u + (kb == 0 ? 2560u : 0u));
+                            ptx::mbar_arrive_expect_tx(&stage_full[stage], stage_bytes);
                             uint8_t* st = smem + (size_t)stage * stage_bytes;
-                            ptx::bulk_load_1d(st + meta_off, p.gm + ((size_t)sl * G + 2 * kb) * 128, 1024u, &stage_full[stage]);
-                            if (kb == 0) {
-                                ptx::bulk_load_1d(st + meta_off + 1024, p.rowcoef + (size_t)sl * 128, 2048u, &stage_full[stage]);
-                                ptx::bulk_load_1d(st + meta_off + 3072, p.rowlab + (size_t)sl * 128, 512u, &stage_full[stage]);
-                            }
                             ptx::tma_load_2d(st, &tmap_e, &stage_full[stage], kb * 64, sl * 128);
                             ptx::tma_load_2d(st + 16384, &tmap_wp, &stage_full[stage], kb * 64, n0);
                             if (sh) ptx::tma_load_2d(st + 16384 + (size_t)priv * 128, &tmap_ws, &stage_full[stage], kb * 64, n0 + priv);
@@ -158,7 +130,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA: D[128 x NCZ] += A[128 x 64] . B[NCZ x 64]^T, both operands K-major in smem =====================
-        const uint32_t idescP = ptx::umma_idesc_f16(128, priv), idescS = ptx::umma_idesc_f16(128, sh ? sh : 16);
+        const uint32_t idescP = ptx::umma_idesc_bf16(128, priv), idescS = ptx::umma_idesc_bf16(128, sh ? sh : 16);
         int stage = 0; uint32_t phase = 0, q = 0;
         for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
             const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
@@ -173,8 +145,6 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     const uint32_t dP = tmem_base + (par ? (uint32_t)p.odd_base : 0u), dS = tmem_base + (uint32_t)priv;
                     for (int kb = 0; kb < KBV; ++kb) {
                         { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_full[stage], phase); RB_PROF_END(pf, pc[1]); }
-                        { RB_PROF_BEGIN(pf); ptx::mbar_wait(&a_ready[stage], phase); RB_PROF_END(pf, pc[2]); }
-                        ptx::tc_fence_after();
                         const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                         const uint64_t ad = ptx::umma_desc_k_sw128(sa), bp = ptx::umma_desc_k_sw128(sa + 16384u),
                                        bs = ptx::umma_desc_k_sw128(sa + 16384u + (uint32_t)priv * 128u);
@@ -188,7 +158,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                             if (kb == 0) {   // the shared zone still holds the previous unit until its epilogue has drained it
                                 RB_PROF_BEGIN(pf);
                                 ptx::mbar_wait(shared_free, (q & 1) ^ 1);
-                                RB_PROF_END(pf, pc[3]);
+                                RB_PROF_END(pf, pc[2]);
                                 ptx::tc_fence_after();
                             }
                             if (ptx::elect_one()) {
@@ -207,53 +177,9 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     }
                 }
         }
-    } else if (warp < 6) {
-        // ===================== A-stage scalers (warps 2-5): thread = lattice row of the tile =====================
-        // everything a scaler needs arrives WITH the stage (bulk copies on the same mbarrier): no global loads, no prefetch logic
-        const int r = threadIdx.x - 64;
-        const uint32_t smem_a = ptx::smem_u32(smem);
-        int stage = 0; uint32_t phase = 0;
-        for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
-            const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
-            const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
-            if (tb * BW_TT >= Tn) continue;
-            const int nub = (Un + BW_UU - 1) / BW_UU;
-            for (int ub = 0; ub < nub; ++ub)
-                for (int pass = 0; pass < NP; ++pass) {
-                    float4 cf = make_float4(0.f, 0.f, 0.f, 0.f);
-                    int lab = -1;
-                    for (int kb = 0; kb < KBV; ++kb) {
-                        { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_full[stage], phase); RB_PROF_END(pf, pc[0]); }
-                        const uint32_t st = smem_a + (uint32_t)stage * stage_bytes, row = st + (uint32_t)r * 128u;
-                        if (kb == 0) {
-                            cf = ptx::lds128f(st + meta_off + 1024u + (uint32_t)r * 16u);
-                            lab = (int)ptx::lds32(st + meta_off + 3072u + (uint32_t)r * 4u);
-                        }
-                        const float g0 = __uint_as_float(ptx::lds32(st + meta_off + (uint32_t)r * 4u)),
-                                    g1 = __uint_as_float(ptx::lds32(st + meta_off + 512u + (uint32_t)r * 4u));
-                        if (!(p.dbg & 2048)) {
-                        uint4 x[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) x[c] = ptx::lds128(row + (uint32_t)((c ^ (r & 7)) << 4));   // eight loads in flight
-                        // (row outside the lattice: cf = (-inf, 0, 0, 0) -> scale 0, specials 0, lab -1)
-                        const __half2 s0 = __float2half2_rn(cf.y * ptx::ex2_approx(g0 + cf.x)), s1 = __float2half2_rn(cf.y * ptx::ex2_approx(g1 + cf.x));
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) ptx::sts128(row + (uint32_t)((c ^ (r & 7)) << 4), scale_chunk(x[c], c < 4 ? s0 : s1));
-                        // the two special columns (blank, label): final values, if they fall inside this K block
-                        const int db = p.blank - kb * 64, dl = lab - kb * 64;
-                        if ((unsigned)db < 64u) ptx::sts16(row + (uint32_t)((((db >> 3) ^ (r & 7)) << 4) + (db & 7) * 2), f16_bits(cf.z));
-                        if ((unsigned)dl < 64u) ptx::sts16(row + (uint32_t)((((dl >> 3) ^ (r & 7)) << 4) + (dl & 7) * 2), f16_bits(cf.w));
-                        }
-                        if (!(p.dbg & 1024)) ptx::fence_proxy_async_smem();
-                        __syncwarp();
-                        if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
-                        if (++stage == DZ_STAGES) { stage = 0; phase ^= 1; }
-                    }
-                }
-        }
     } else {
-        // ===================== epilogue (warps 6-13): g = acc * (1 - tanh^2), tile sums =====================
-        const int qd = warp & 3, hh = (warp - 6) >> 2, qslot = (warp - 6) & 3;
+        // ===================== epilogue (warps 2-9): g = rs_row * acc * (1 - tanh^2), tile sums =====================
+        const int qd = warp & 3, hh = (warp - 2) >> 2, qslot = (warp - 2) & 3;
         const int r = qd * 32 + lane, ul = lane & 7;
         const int npr = priv >> 5, nsh = sh >> 5;                  // 32-column chunks of the private / shared zone
         const int nsh_h = nsh >> 1, npr_h = (npr - hh + 1) >> 1;   // this warp's share (chunks with index % 2 == hh)
@@ -261,7 +187,6 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         const uint32_t dp0 = ptx::smem_u32(dpb) + (uint32_t)hh * 2 * DP_ONE * 4;
         const int off4 = (ul & 1) * 16 + ((ul >> 1) & 1) * 8 + ((ul >> 2) & 1) * 4;   // columns this lane keeps after the u butterfly
         const int cbase = ((lane >> 3) & 1) * 16 + ((lane >> 4) & 1) * 8;              // ... after the t butterfly
-        const float inv_s = p.gscale[1];
         uint32_t q = 0, nchunk = 0;
         for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
             const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
@@ -280,6 +205,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
             for (int ub = 0; ub < nub; ++ub) {
                 const int u = ub * BW_UU + ul;
                 const float* prow = p.pred + ((size_t)b * p.maxU + min(u, p.maxU - 1)) * p.H;
+                const int tile = (bl * p.nTb + tb) * p.nUb + ub;
+                const float rs = __ldg(p.rowscale + (size_t)(p.slot ? p.slot[tile] : tile) * 128 + r);   // 0 outside the lattice
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass >= NP) continue;
@@ -313,8 +240,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                                 const float4 e = __ldg(e4 + i), qq = __ldg(q4 + i);
                                 const float z0 = ptx::tanh_approx(e.x + qq.x), z1 = ptx::tanh_approx(e.y + qq.y),
                                             z2 = ptx::tanh_approx(e.z + qq.z), z3 = ptx::tanh_approx(e.w + qq.w);
-                                const float d0 = __uint_as_float(v[4 * i]) * inv_s, d1 = __uint_as_float(v[4 * i + 1]) * inv_s,
-                                            d2 = __uint_as_float(v[4 * i + 2]) * inv_s, d3 = __uint_as_float(v[4 * i + 3]) * inv_s;
+                                const float d0 = __uint_as_float(v[4 * i]) * rs, d1 = __uint_as_float(v[4 * i + 1]) * rs,
+                                            d2 = __uint_as_float(v[4 * i + 2]) * rs, d3 = __uint_as_float(v[4 * i + 3]) * rs;
                                 g[4 * i] = fmaf(-d0 * z0, z0, d0); g[4 * i + 1] = fmaf(-d1 * z1, z1, d1);
                                 g[4 * i + 2] = fmaf(-d2 * z2, z2, d2); g[4 * i + 3] = fmaf(-d3 * z3, z3, d3);
                             }
@@ -391,9 +318,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
             }
         }
     }
-    if (pf) {   // [role 0..3][total, wait0..3]: role = TMA, MMA, scaler warp 2, epilogue warp 6
-        const int role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3;
-        long long* o = p.prof + ((size_t)blockIdx.x * 4 + role) * 8;
+    if (pf) {   // [role 0..2][total, wait0..3]: role = TMA, MMA, epilogue warp 2
+        long long* o = p.prof + ((size_t)blockIdx.x * 4 + warp) * 8;
         o[0] = clock64() - t_start; o[1] = pc[0]; o[2] = pc[1]; o[3] = pc[2]; o[4] = pc[3];
     }
     ptx::tc_fence_before();
@@ -425,8 +351,8 @@ __global__ void __launch_bounds__(256) sum_pred_planes_kernel(const float4* __re
 // dW kernel
 // ---------------------------------------------------------------------------------------------------------------
 // CTA = (v-tile of DW_NV columns, h-item, split of the K = lattice-row range).  An h-item owns two block slots of 128 output
-// rows; the block list is [h-block 0 .. nHB-1, ONES]: the ONES block is an A tile whose row 0 is all ones, so that row 0
-// of its product is db = sum_rows dl (H = 640: items (0,1) (2,3) (4,ONES) -- three equal units of work per v-tile).
+// rows; the block list is [h-block 0 .. nHB-1, SCALE]: the SCALE block is an A tile whose row 0 holds the row scales, so that
+// row 0 of its product is db = sum_rows dl (H = 640: items (0,1) (2,3) (4,SCALE) -- three equal units of work per v-tile).
 // K step = half a tile (64 lattice rows: 8 time steps x 8 label positions).
 struct DwWork { int vt, item, split; };
 __device__ __forceinline__ DwWork dw_decode(const BwdParams& p, int cta) {
@@ -438,7 +364,7 @@ __device__ __forceinline__ DwWork dw_decode(const BwdParams& p, int cta) {
     w.split = rem - w.item * p.S;
     return w;
 }
-// block slot k2 of an item: index into [h-block 0 .. nHB-1, ONES]; kind 0 = h-block, 1 = ONES, 2 = none
+// block slot k2 of an item: index into [h-block 0 .. nHB-1, SCALE]; kind 0 = h-block, 1 = SCALE, 2 = none
 __device__ __forceinline__ int dw_kind(const BwdParams& p, int item, int k2) {
     const int blk = 2 * item + k2;
     return blk < p.nHB ? 0 : (blk == p.nHB ? 1 : 2);
@@ -447,35 +373,34 @@ __device__ __forceinline__ int dw_kind(const BwdParams& p, int item, int k2) {
 __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_constant__ CUtensorMap tmap_e, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // stage = A: 2 x [128 h x 64 k] K-major (32 KB) | B: 4 x [64 k x 64 v] MN-major (32 KB) | meta (4 KB): gm of the stage's 64
-    // rows x 8 column groups (8 x 256 B), the rows' coefficients (64 x float4) and label columns (64 x int)
-    constexpr uint32_t STAGE = 65536u + 4096u, META = 65536u;
-    uint8_t* ones = smem + DW_STAGES * STAGE;                               // [128 x 64] fp16 K-major SW128, row 0 = 1.0
-    uint32_t* tab = reinterpret_cast<uint32_t*>(ones + 16384);              // { sc[64][8] half2, specz[64], specw[64], labc[64] }
-    constexpr int TAB_ONE = 64 * 8 + 3 * 64;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tab + TAB_ONE);
-    uint64_t* b_full = bars;                       // [DW_STAGES] TMA -> scalers
-    uint64_t* b_ready = b_full + DW_STAGES;        // scalers -> MMA
-    uint64_t* a_ready = b_ready + DW_STAGES;       // producers -> MMA
-    uint64_t* stage_empty = a_ready + DW_STAGES;   // MMA -> TMA, producers
+    // stage = A: 2 x [128 x 64 k] K-major (32 KB) | B: 4 x [64 k x 64 v] MN-major (32 KB) | the 64 rows' scales (256 B, padded to 1 KB)
+    constexpr uint32_t STAGE = 65536u + 1024u, META = 65536u;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DW_STAGES * STAGE);
+    uint64_t* b_full = bars;                       // [DW_STAGES] TMA -> producers, MMA
+    uint64_t* a_ready = b_full + DW_STAGES;        // producers -> MMA
+    uint64_t* stage_empty = a_ready + DW_STAGES;   // MMA -> TMA
     uint64_t* acc_full = stage_empty + DW_STAGES;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const DwWork wk = dw_decode(p, blockIdx.x);
-    const int v0 = wk.vt * DW_NV, Nv = min(DW_NV, p.V - v0), nbox = Nv >> 6, G = p.V >> 5;
+    const int v0 = wk.vt * DW_NV, Nv = min(DW_NV, p.V - v0), nbox = Nv >> 6;
     const int kind0 = dw_kind(p, wk.item, 0), kind1 = dw_kind(p, wk.item, 1);
-    const int nprod = (kind0 == 0) + (kind1 == 0);                         // block slots fed by producer warps
+    const int narr = 4 * ((kind0 == 0) + (kind1 == 0)) + (kind0 == 1) + (kind1 == 1);   // warps that arrive on a_ready per K step
     if (threadIdx.x == 0) {
         for (int i = 0; i < DW_STAGES; ++i) {
-            ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&b_ready[i], 4);
-            ptx::mbar_init(&a_ready[i], nprod ? 4 * nprod : 1); ptx::mbar_init(&stage_empty[i], 1);
+            ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&a_ready[i], narr ? narr : 1); ptx::mbar_init(&stage_empty[i], 1);
         }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
-    for (int i = threadIdx.x; i < 16384 / 16; i += DW_THREADS)            // row 0 (the first 128 bytes) = fp16 1.0, the rest 0
-        reinterpret_cast<uint4*>(ones)[i] = i < 8 ? make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u) : make_uint4(0u, 0u, 0u, 0u);
+    // the SCALE block's A tile: rows 1..127 stay zero for the whole kernel, row 0 is rewritten every K step
+#pragma unroll
+    for (int k2 = 0; k2 < 2; ++k2)
+        if ((k2 ? kind1 : kind0) == 1)
+            for (int st = 0; st < DW_STAGES; ++st)
+                for (int i = threadIdx.x; i < 16384 / 16; i += DW_THREADS)
+                    reinterpret_cast<uint4*>(smem + (size_t)st * STAGE + k2 * 16384)[i] = make_uint4(0u, 0u, 0u, 0u);
     ptx::fence_proxy_async_smem();
     if (warp == 1) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
     if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_e);
@@ -486,46 +411,41 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
     const long long cnt = *p.count;
     const int s_beg = (int)(cnt * wk.split / p.S), s_end = (int)(cnt * (wk.split + 1) / p.S);
     const int per_utt = p.nTb * p.nUb;
-    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2 || warp == 6);
+    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);
     long long pc[4] = {0, 0, 0, 0};
     const long long t_start = pf ? clock64() : 0;
 
     if (warp == 0) {
-        // ===================== TMA: B = kept numerators, boxes [64 rows x 64 v] (rows = K) =====================
+        // ===================== TMA: B = kept numerators, boxes [64 rows x 64 v] (rows = K), + the rows' scales =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
             for (int s = s_beg; s < s_end; ++s)
                 for (int half = 0; half < 2; ++half) {
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
-                    ptx::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)nbox * (8192u + 512u) + 1024u + 256u);
+                    ptx::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)nbox * 8192u + 256u);
                     uint8_t* bs = smem + (size_t)stage * STAGE + 32768;
-                    uint8_t* mt = smem + (size_t)stage * STAGE + META;
-                    for (int j = 0; j < 2 * nbox; ++j)
-                        ptx::bulk_load_1d(mt + j * 256, p.gm + ((size_t)s * G + (v0 >> 5) + j) * 128 + half * 64, 256u, &b_full[stage]);
-                    ptx::bulk_load_1d(mt + 2048, p.rowcoef + (size_t)s * 128 + half * 64, 1024u, &b_full[stage]);
-                    ptx::bulk_load_1d(mt + 3072, p.rowlab + (size_t)s * 128 + half * 64, 256u, &b_full[stage]);
+                    ptx::bulk_load_1d(smem + (size_t)stage * STAGE + META, p.rowscale + (size_t)s * 128 + half * 64, 256u, &b_full[stage]);
                     for (int j = 0; j < nbox; ++j)
                         ptx::tma_load_2d(bs + j * 8192, &tmap_e, &b_full[stage], v0 + 64 * j, s * 128 + half * 64);
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
                 }
         }
     } else if (warp == 1) {
-        // ===================== MMA: D[slot][128 x Nv] += A[128 x 64 k] . dl[64 k x Nv]  (A K-major, B MN-major) =====================
-        const uint32_t idesc = ptx::umma_idesc_f16(128, Nv, 0, 1);
+        // ===================== MMA: D[slot][128 x Nv] += A[128 x 64 k] . E'[64 k x Nv]  (A K-major, B MN-major) =====================
+        const uint32_t idesc = ptx::umma_idesc_bf16(128, Nv, 0, 1);
         int stage = 0; uint32_t phase = 0, it = 0;
         for (int s = s_beg; s < s_end; ++s)
             for (int half = 0; half < 2; ++half, ++it) {
-                { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_ready[stage], phase); RB_PROF_END(pf, pc[0]); }
-                if (nprod) { RB_PROF_BEGIN(pf); ptx::mbar_wait(&a_ready[stage], phase); RB_PROF_END(pf, pc[1]); }
+                { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_full[stage], phase); RB_PROF_END(pf, pc[0]); }
+                if (narr) { RB_PROF_BEGIN(pf); ptx::mbar_wait(&a_ready[stage], phase); RB_PROF_END(pf, pc[1]); }
                 ptx::tc_fence_after();
                 const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * STAGE);
                 const uint64_t bd = ptx::umma_desc_mn_sw128(sa + 32768u, 8192u);
                 if (ptx::elect_one()) {
 #pragma unroll
                     for (int k2 = 0; k2 < 2; ++k2) {
-                        const int kd = k2 ? kind1 : kind0;
-                        if (kd != 2) {
-                            const uint64_t ad = ptx::umma_desc_k_sw128(kd == 1 ? ptx::smem_u32(ones) : sa + (uint32_t)k2 * 16384u);
+                        if ((k2 ? kind1 : kind0) != 2) {
+                            const uint64_t ad = ptx::umma_desc_k_sw128(sa + (uint32_t)k2 * 16384u);
 #pragma unroll
                             for (int k = 0; k < 4; ++k)   // K = 16 lattice rows per MMA: 32 B along A's rows, 16 x 128 B of B
                                 ptx::umma_bf16(tmem_base + (uint32_t)k2 * DW_NV, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 128),
@@ -538,126 +458,82 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                 __syncwarp();
                 if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
             }
-    } else if (warp < 6) {
-        // ===================== B-stage scalers (warps 2-5) =====================
-        // The per-row inputs (coefficients, label column, the running maxima of the 8 column groups) arrive WITH the stage.
-        // Threads 0-63 turn them into a table of half2 scales per (row, group); then every thread scales its chunks.
-        const int r4 = threadIdx.x - 64, c = r4 & 31, rg = r4 >> 5;     // 16-byte chunk of the 512-byte row | group of 16 rows
-        int stage = 0; uint32_t phase = 0;
-        const int dbk = p.blank - v0 - c * 8;
-        const uint32_t smem_a = ptx::smem_u32(smem), tba = ptx::smem_u32(tab);
-        for (int s = s_beg; s < s_end; ++s)
-            for (int half = 0; half < 2; ++half) {
-                { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_full[stage], phase); RB_PROF_END(pf, pc[1]); }
-                const uint32_t mt = smem_a + (uint32_t)stage * STAGE + META;
-                { RB_PROF_BEGIN(pf); ptx::named_bar_sync(3, 128); RB_PROF_END(pf, pc[0]); }     // the previous step's table reads are done
-                if (r4 < 64) {
-                    const float4 cf = ptx::lds128f(mt + 2048u + (uint32_t)r4 * 16u);
-                    const int lab = (int)ptx::lds32(mt + 3072u + (uint32_t)r4 * 4u);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {   // (row outside the lattice: g = 0, kd = -inf -> scale 0)
-                        const float gmv = i < 2 * nbox ? __uint_as_float(ptx::lds32(mt + (uint32_t)(i * 256 + r4 * 4))) : 0.f;
-                        const __half2 h2 = __float2half2_rn(cf.y * ptx::ex2_approx(gmv + cf.x));
-                        ptx::sts32(tba + (uint32_t)((r4 * 8 + i) * 4), *reinterpret_cast<const uint32_t*>(&h2));
-                    }
-                    ptx::sts32(tba + (uint32_t)((512 + r4) * 4), __float_as_uint(cf.z));
-                    ptx::sts32(tba + (uint32_t)((576 + r4) * 4), __float_as_uint(cf.w));
-                    ptx::sts32(tba + (uint32_t)((640 + r4) * 4), (uint32_t)(lab >= 0 ? lab - v0 : -100000));
-                }
-                ptx::named_bar_sync(3, 128);
-                const uint32_t bs = smem_a + (uint32_t)stage * STAGE + 32768u + (uint32_t)(c >> 3) * 8192u;
-                if ((c >> 3) < nbox && !(p.dbg & 2048)) {
-#pragma unroll
-                    for (int r0 = 0; r0 < 16; r0 += 8) {            // two batches of eight rows: all loads of a batch in flight together
-                        uint4 x[8]; uint32_t sc[8], lc[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = rg * 16 + r0 + j;
-                            x[j] = ptx::lds128(bs + (uint32_t)(k * 128 + (((c & 7) ^ (k & 7)) << 4)));
-                            sc[j] = ptx::lds32(tba + (uint32_t)((k * 8 + (c >> 2)) * 4));
-                            lc[j] = ptx::lds32(tba + (uint32_t)((640 + k) * 4));
-                        }
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int k = rg * 16 + r0 + j;
-                            const uint32_t a = bs + (uint32_t)(k * 128 + (((c & 7) ^ (k & 7)) << 4));
-                            ptx::sts128(a, scale_chunk(x[j], *reinterpret_cast<const __half2*>(&sc[j])));
-                            const int dl = (int)lc[j] - c * 8;       // special columns of row k that fall inside this chunk: final values
-                            if ((unsigned)dbk < 8u) ptx::sts16(a + (uint32_t)(dbk * 2), f16_bits(__uint_as_float(ptx::lds32(tba + (uint32_t)((512 + k) * 4)))));
-                            if ((unsigned)dl < 8u) ptx::sts16(a + (uint32_t)(dl * 2), f16_bits(__uint_as_float(ptx::lds32(tba + (uint32_t)((576 + k) * 4)))));
-                        }
-                    }
-                }
-                if (!(p.dbg & 1024)) ptx::fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&b_ready[stage]);
-                if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
-            }
     } else {
-        // ===================== z producers (warps 6-13): thread = column h of the joint; then the epilogue =====================
-        const int ptid = threadIdx.x - 192, k2 = ptid >> 7, hl = ptid & 127;
+        // ===================== A producers (warps 2-9): thread = column h of the joint (or the SCALE row); then the epilogue =====================
+        const int ptid = threadIdx.x - 64, k2 = ptid >> 7, hl = ptid & 127;
         const int kind = k2 ? kind1 : kind0, hb = 2 * wk.item + k2;
         const int h = hb * 128 + hl;
         const bool hv = kind == 0 && h < p.H;
+        const uint32_t smem_a = ptx::smem_u32(smem);
         if (kind == 0) {
-            // Inputs of slot s+1 (its tile's 8 pred rows and 16 enc rows of this thread's column h, the lengths) are loaded
-            // while slot s is computed; the tile id is read two slots ahead, so no load waits on another load.
-            struct Tl { int b, t0, u0, Tn, Un; };
-            auto decode = [&](int tile) {
-                Tl t;
-                const int bl = tile / per_utt, rem = tile - bl * per_utt;
-                t.b = p.b0 + bl; t.t0 = (rem / p.nUb) * BW_TT; t.u0 = (rem % p.nUb) * BW_UU;
-                t.Tn = p.xlen[t.b]; t.Un = p.ylen[t.b] + 1;
-                return t;
-            };
+            // Inputs of slot s+1 (its tile's 8 pred rows and 16 enc rows of this thread's column h) are loaded while slot s is
+            // computed; the tile id is read two slots ahead, so no load waits on another load.  Rows outside the lattice
+            // carry rs = 0, so no length test is needed here.
             auto tile_at = [&](int s) { return s < s_end ? (p.tile_of_slot ? p.tile_of_slot[s] : s) : 0; };
-            Tl cur = decode(tile_at(s_beg)), nxt = cur;
             float pv[8], ev[16], npv[8], nev[16];
-            auto load = [&](const Tl& t, float* pvv, float* evv) {
+            auto load = [&](int tile, float* pvv, float* evv) {
+                const int bl = tile / per_utt, rem = tile - bl * per_utt, b = p.b0 + bl;
+                const int t0 = (rem / p.nUb) * BW_TT, u0 = (rem % p.nUb) * BW_UU;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) pvv[k] = hv ? __ldg(p.pred + ((size_t)t.b * p.maxU + min(t.u0 + k, p.maxU - 1)) * p.H + h) : 0.f;
+                for (int k = 0; k < 8; ++k) pvv[k] = hv ? __ldg(p.pred + ((size_t)b * p.maxU + min(u0 + k, p.maxU - 1)) * p.H + h) : 0.f;
 #pragma unroll
-                for (int k = 0; k < 16; ++k) evv[k] = hv ? __ldg(p.enc + ((size_t)t.b * p.maxT + min(t.t0 + k, p.maxT - 1)) * p.H + h) : 0.f;
+                for (int k = 0; k < 16; ++k) evv[k] = hv ? __ldg(p.enc + ((size_t)b * p.maxT + min(t0 + k, p.maxT - 1)) * p.H + h) : 0.f;
             };
-            load(cur, pv, ev);
+            load(tile_at(s_beg), pv, ev);
             int tile_n = tile_at(s_beg + 1);
             int stage = 0; uint32_t phase = 0;
             for (int s = s_beg; s < s_end; ++s) {
                 const int tile_nn = tile_at(s + 2);
-                if (s + 1 < s_end) { nxt = decode(tile_n); load(nxt, npv, nev); }
+                if (s + 1 < s_end) load(tile_n, npv, nev);
                 for (int half = 0; half < 2; ++half) {
-                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
-                    const uint32_t arow = ptx::smem_u32(smem) + (uint32_t)stage * STAGE + (uint32_t)(k2 * 16384 + hl * 128);
+                    // b_full also says that the previous contents of the stage were consumed (the TMA waited for stage_empty)
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_full[stage], phase); RB_PROF_END(pf, pc[0]); }
+                    const uint32_t arow = smem_a + (uint32_t)stage * STAGE + (uint32_t)(k2 * 16384 + hl * 128);
+                    const uint32_t rsa = smem_a + (uint32_t)stage * STAGE + META;
 #pragma unroll
                     for (int tl = 0; tl < 8; ++tl) {
-                        const bool tv = hv && (cur.t0 + half * 8 + tl) < cur.Tn;
                         const float e = half ? ev[8 + tl] : ev[tl];
+                        const float4 r0 = ptx::lds128f(rsa + (uint32_t)(tl * 32)), r1 = ptx::lds128f(rsa + (uint32_t)(tl * 32 + 16));   // rs of rows tl*8 .. +7
+                        const float rsv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                         float z[8];
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) z[k] = (tv && (cur.u0 + k) < cur.Un) ? ptx::tanh_approx(e + pv[k]) : 0.f;
+                        for (int k = 0; k < 8; ++k) z[k] = ptx::tanh_approx(e + pv[k]) * rsv[k];
                         ptx::sts128(arow + (uint32_t)((tl ^ (hl & 7)) << 4),
-                                    make_uint4(ptx::pack_f16x2(z[0], z[1]), ptx::pack_f16x2(z[2], z[3]), ptx::pack_f16x2(z[4], z[5]),
-                                               ptx::pack_f16x2(z[6], z[7])));
+                                    make_uint4(ptx::pack_bf16x2(z[0], z[1]), ptx::pack_bf16x2(z[2], z[3]), ptx::pack_bf16x2(z[4], z[5]),
+                                               ptx::pack_bf16x2(z[6], z[7])));
                     }
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
                 }
-                cur = nxt; tile_n = tile_nn;
+                tile_n = tile_nn;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) pv[k] = npv[k];
 #pragma unroll
                 for (int k = 0; k < 16; ++k) ev[k] = nev[k];
             }
+        } else if (kind == 1 && hl < 32) {
+            // SCALE block: one warp copies the stage's 64 row scales (bf16) into row 0 of the slot's A tile (row 0: no swizzle)
+            int stage = 0; uint32_t phase = 0;
+            for (int s = s_beg; s < s_end; ++s)
+                for (int half = 0; half < 2; ++half) {
+                    ptx::mbar_wait(&b_full[stage], phase);
+                    const uint32_t st = smem_a + (uint32_t)stage * STAGE;
+                    const float2 x = ptx::lds64f(st + META + (uint32_t)lane * 8u);
+                    ptx::sts32(st + (uint32_t)(k2 * 16384) + (uint32_t)lane * 4u, ptx::pack_bf16x2(x.x, x.y));
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+                    if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
+                }
         }
-        // ---- epilogue: this warp's 32 rows of block slot k2, Nv columns -> the split's partial plane (times 1/S)
+        // ---- epilogue: this warp's 32 rows of block slot k2, Nv columns -> accumulated into the split's partial plane
         if (kind != 2 && s_end > s_beg) {
             { RB_PROF_BEGIN(pf); ptx::mbar_wait(acc_full, 0); RB_PROF_END(pf, pc[1]); }
             ptx::tc_fence_after();
-            const float inv_s = p.gscale[1];
             const int qd = warp & 3, hr = hb * 128 + qd * 32 + lane;
-            // h-block: row hr of the dW plane; ONES block: only TMEM lane 0 carries data (db)
+            // h-block: row hr of the dW plane; SCALE block: only TMEM lane 0 carries data (db)
             const bool on = kind == 0 ? hr < p.Hrows : (qd == 0 && lane == 0);
             float* dst = kind == 0 ? p.dWp + ((size_t)wk.split * p.Hrows + hr) * p.V + v0 : p.dbp + (size_t)wk.split * p.V + v0;
             if (kind == 0 || qd == 0) {
@@ -670,17 +546,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                         for (int i = 0; i < 8; ++i) {
                             float4* d4 = reinterpret_cast<float4*>(dst + j * 32 + i * 4);
                             const float4 x = *d4;
-                            *d4 = make_float4(fmaf(__uint_as_float(v[4 * i]), inv_s, x.x), fmaf(__uint_as_float(v[4 * i + 1]), inv_s, x.y),
-                                              fmaf(__uint_as_float(v[4 * i + 2]), inv_s, x.z), fmaf(__uint_as_float(v[4 * i + 3]), inv_s, x.w));
+                            *d4 = make_float4(__uint_as_float(v[4 * i]) + x.x, __uint_as_float(v[4 * i + 1]) + x.y,
+                                              __uint_as_float(v[4 * i + 2]) + x.z, __uint_as_float(v[4 * i + 3]) + x.w);
                         }
                     }
                 }
             }
         }
     }
-    if (pf) {   // [role 0..3][total, wait0, wait1]: role = TMA, MMA, scaler warp 2, producer warp 6
-        const int role = warp == 0 ? 0 : warp == 1 ? 1 : warp == 2 ? 2 : 3;
-        long long* o = p.prof + ((size_t)blockIdx.x * 4 + role) * 8;
+    if (pf) {   // [role 0..2][total, wait0, wait1]: role = TMA, MMA, producer warp 2
+        long long* o = p.prof + ((size_t)blockIdx.x * 4 + warp) * 8;
         o[0] = clock64() - t_start; o[1] = pc[0]; o[2] = pc[1]; o[3] = pc[2]; o[4] = pc[3];
     }
     ptx::tc_fence_before();

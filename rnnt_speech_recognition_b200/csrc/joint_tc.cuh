@@ -75,8 +75,8 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
     g.sh = 2 * g.NCZ > 512 ? 2 * g.NCZ - 512 : 0;
     g.priv = g.NCZ - g.sh;
     g.odd_base = 512 - g.priv;
-    g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128 + 4096) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
-    g.dw_smem = 1024 + (size_t)3 * (65536 + 4096) + 16384 + (size_t)(64 * 8 + 3 * 64) * 4 + 512;
+    g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+    g.dw_smem = 1024 + (size_t)3 * (65536 + 1024) + 512;
     g.nHB = (H + 127) / 128;
     g.nItems = (g.nHB + 2) / 2;               // blocks [0 .. nHB-1, ONES] in pairs
     g.nVT = (V + 255) / 256;
@@ -116,7 +116,7 @@ __device__ __forceinline__ TileInfo decode_tile(const JointTcParams& p, int tile
     return ti;
 }
 
-// W (H,V) fp32 -> Wt (V,H) fp16 [B operand of the logits GEMM, K=h] and Wb (H,V) fp16 [B operand of dZ, K=v]
+// W (H,V) fp32 -> Wt (V,H) fp16 [B operand of the logits GEMM, K=h] and Wb (H,V) bf16 [B operand of dZ, K=v]
 __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict__ W, __nv_bfloat16* __restrict__ Wt,
                                                         __nv_bfloat16* __restrict__ Wb, int H, int V) {
     __shared__ float tile[32][33];
@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
         const int h = h0 + i, v = v0 + tx;
         const float w = (h < H && v < V) ? W[(size_t)h * V + v] : 0.f;
         tile[i][tx] = w;
-        if (h < H && v < V) reinterpret_cast<__half*>(Wb)[(size_t)h * V + v] = __float2half_rn(w);
+        if (h < H && v < V) Wb[(size_t)h * V + v] = __float2bfloat16(w);
     }
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
@@ -252,17 +252,16 @@ inline bool make_tmap_f32(CUtensorMap* tm, const void* base, uint64_t rows, uint
 // Workspace of the tensor-core path (a pure function of the descriptor).  The kept arrays (numerators + maxima) are
 // laid out per 128-row tile; the batch is processed in utterance chunks that keep them under ~16 GiB.
 struct TcScratch {
-    __nv_bfloat16 *Wt, *Wb;                 // W^T (V,H) fp16 [forward B operand] and W (H,V) fp16 [dZ B operand] (16-bit storage)
-    __nv_bfloat16* dl;                      // (rows_chunk, V) fp16 softmax numerators 2^(y - m)
-    float* gm;                              // (row blocks, V/32, 128) fp32 running maxima m (log2 domain)
+    __nv_bfloat16 *Wt, *Wb;                 // W^T (V,H) fp16 [forward B operand, 16-bit storage] and W (H,V) bf16 [dZ B operand]
+    __nv_bfloat16* dl;                      // (rows_chunk, V) bf16 softmax numerators E = 2^(y - ref_row)
+    float* gm;                              // (rows_chunk) fp32 reference of each row's numerators (log2 domain)
     int* slot;                              // tile -> compact row block (-1: outside the valid lattice), per chunk
     int* tile_of_slot;                      // compact row block -> tile
     int* count;                             // number of valid tiles of the chunk
     float* ppl;                             // (nTb, bchunk, maxU, H) fp32 partial planes of d_pred (bwd_dz_kernel)
     float* dWp;                             // (S_max, H, V) fp32 split-K planes of dW (bwd_dw_kernel)
     float* dbp;                             // (S_max, V) planes of db
-    float4* rowcoef;                        // (rows_chunk) per-row backward coefficients (row_coef_kernel)
-    int* rowlab;                            // (rows_chunk) label column of the row or -1
+    float* rowscale;                        // (rows_chunk) per-row scale of the logit gradients (row_scale_kernel)
     int bchunk;                             // utterances per chunk
     size_t rows_chunk;                      // bchunk * tiles_per_utt * 128
     size_t bytes;
@@ -279,7 +278,7 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     const BwdGeom bg = bwd_geometry(d.H, d.V);
     const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
-    const size_t per_row = (size_t)d.V * 2 + (size_t)(d.V / 32) * 4;
+    const size_t per_row = (size_t)d.V * 2 + 8;
     size_t bc = tc_chunk_budget() / (rows_utt * per_row);
     if (bc < 1) bc = 1;
     if (bc > (size_t)d.B) bc = d.B;
@@ -290,15 +289,14 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.Wb = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
     s.dl = reinterpret_cast<__nv_bfloat16*>(take(s.rows_chunk * d.V * 2));
-    s.gm = reinterpret_cast<float*>(take(s.rows_chunk * (size_t)(d.V / 32) * 4));
+    s.gm = reinterpret_cast<float*>(take(s.rows_chunk * 4));
     s.slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
     s.tile_of_slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
     s.count = reinterpret_cast<int*>(take(256));
     s.ppl = reinterpret_cast<float*>(take((size_t)g.nTb * bc * d.maxU * d.H * 4));
     s.dWp = reinterpret_cast<float*>(take((size_t)bg.S_max * d.H * d.V * 4));
     s.dbp = reinterpret_cast<float*>(take((size_t)bg.S_max * d.V * 4));
-    s.rowcoef = reinterpret_cast<float4*>(take(s.rows_chunk * 16));
-    s.rowlab = reinterpret_cast<int*>(take(s.rows_chunk * 4));
+    s.rowscale = reinterpret_cast<float*>(take(s.rows_chunk * 4));
     s.bytes = (size_t)(p - static_cast<char*>(base));
     return s;
 }
@@ -434,8 +432,8 @@ struct LossPlanes { const float *lse, *lpb, *lpl, *alphas, *betas, *llf; };   //
 // synchronisation, no library calls.
 inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const float* enc, const float* pred,
                                 const float* bias, const int* labels, const int* ylen, const int* xlen,
-                                const LossPlanes& lp, const float* grad_costs, float* gscale, float* d_enc, float* d_pred,
-                                float* dW, float* db, cudaStream_t s, unsigned* launches) {
+                                const LossPlanes& lp, const float* grad_costs, float* d_enc, float* d_pred, float* dW,
+                                float* db, cudaStream_t s, unsigned* launches) {
     if (!tc_supported(d)) return tc_unsupported(d);
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
     const BwdGeom bg = bwd_geometry(d.H, d.V);
@@ -443,8 +441,6 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     const bool kept = tc_keep(d, sc);
     if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel)))
         return RNNT_STATUS_EXECUTION_FAILED;
-    gscale_kernel<<<1, 256, 0, s>>>(grad_costs, d.B, gscale);
-    *launches += 1;
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
         return RNNT_STATUS_MEMOPS_FAILED;
@@ -462,22 +458,22 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             if (st) return st;
         }
         BwdParams p{};
-        p.enc = enc; p.pred = pred; p.labels = labels; p.xlen = xlen; p.ylen = ylen;
-        p.maxT = d.maxT; p.maxU = d.maxU; p.H = d.H; p.V = d.V; p.blank = d.blank_label;
+        p.enc = enc; p.pred = pred; p.xlen = xlen; p.ylen = ylen;
+        p.maxT = d.maxT; p.maxU = d.maxU; p.H = d.H; p.V = d.V;
         p.nTb = g.nTb; p.nUb = g.nUb; p.b0 = b0; p.nb = nb;
-        {   // per-row coefficients of this chunk, in the row order of the kept arrays
-            ScopedTimer tmr("row_coef_kernel", s);
-            row_coef_kernel<<<(unsigned)(((size_t)nb * g.nTb * g.nUb * 128 + 255) / 256), 256, 0, s>>>(
+        {   // per-row scales of this chunk (row order of the kept arrays) + the two special columns of every row
+            ScopedTimer tmr("row_scale_kernel", s);
+            row_scale_kernel<<<(unsigned)(((size_t)nb * g.nTb * g.nUb * 128 + 255) / 256), 256, 0, s>>>(
                 sc.tile_of_slot, sc.count, b0, g.nTb, g.nUb, xlen, ylen, labels, d.blank_label, d.maxT, d.maxU,
-                (long long)(d.maxT + d.maxU - 1) * d.maxU, lp.lse, lp.lpb, lp.lpl, lp.alphas, lp.betas, lp.llf, grad_costs, gscale,
-                sc.rowcoef, sc.rowlab);
+                (long long)(d.maxT + d.maxU - 1) * d.maxU, lp.lse, lp.lpb, lp.lpl, lp.alphas, lp.betas, lp.llf, grad_costs, sc.gm,
+                d.V, reinterpret_cast<unsigned short*>(sc.dl), sc.rowscale);
             *launches += 1;
         }
-        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.rowcoef = sc.rowcoef; p.rowlab = sc.rowlab; p.gm = sc.gm;
+        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.rowscale = sc.rowscale;
         p.NP = bg.NP; p.NCZ = bg.NCZ; p.priv = bg.priv; p.sh = bg.sh; p.odd_base = bg.odd_base;
         p.d_enc = d_enc; p.ppred = sc.ppl;
         p.nVT = bg.nVT; p.nItems = bg.nItems; p.nHB = bg.nHB; p.S = bg.S_max; p.Hrows = d.H;
-        p.dWp = sc.dWp; p.dbp = sc.dbp; p.gscale = gscale; p.dbg = tc_dbg();
+        p.dWp = sc.dWp; p.dbp = sc.dbp;
         long long* prof_dz = tc_prof_buffer(0), *prof_dw = tc_prof_buffer(1);
         // rows of d_enc whose t-block lies outside the utterance are never visited by the dZ kernel
         if (cudaMemsetAsync(d_enc + (size_t)b0 * d.maxT * d.H, 0, sizeof(float) * (size_t)nb * d.maxT * d.H, s) != cudaSuccess)

@@ -16,8 +16,11 @@
 //
 // MODE 0  forward: lse + (blank, label) log-probs per cell; nothing else leaves the SM
 // MODE 2  forward that KEEPS its activations (rnntb200JointDesc.keep_activations, and the backward's per-chunk
-//         recompute): MODE 0 + the fp16 softmax numerators 2^(y - m) the epilogue computes anyway and the running
-//         maxima m per 32-column group; bwd_tc.cuh turns them into logit gradients inside its GEMM prologues.
+//         recompute): MODE 0 + the softmax numerators E[row, v] = 2^(y_v - ref_row) as bf16, all columns of a row against
+//         ONE reference ref_row = the maximum of the row's first 32 logits (bf16 keeps its 8 significant bits over the whole
+//         exponent range, so any reference works; the exponent is clamped at +100), and ref_row itself.  The logit
+//         gradients are then row_scale * E: the two backward GEMMs take E straight from TMA and apply the row scale in an
+//         epilogue (dZ) or to the regenerated A operand (dW) -- no per-element prologue.
 #pragma once
 #include <cuda_fp16.h>
 #include "joint_tc.cuh"
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
             const bool rv = t < ti.Tn && u < ti.Un;
             const int lab = (rv && u < ti.Un - 1) ? p.labels[(size_t)ti.b * (p.maxU - 1) + u] : -1;
             const long long cell = ((long long)ti.b * p.maxT + t) * p.maxU + u;
-            float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f;
+            float m2 = -CUDART_INF_F, s = 0.f, yb = 0.f, yl = 0.f, ref = 0.f;
             const uint32_t lane_addr = acc0 + ((uint32_t)(warp * 32) << 16);
             for (int c = 0; c < NCH; ++c, ++g) {
                 const uint32_t buf = g % NBUF, use = g / NBUF;
@@ -301,18 +304,31 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                             for (int i = 0; i < 32; i += 2)   // (same order of additions as MODE 2: the two modes return identical bits)
                                 acc += ptx::ex2_approx(y[i] - mn) + ptx::ex2_approx(y[i + 1] - mn);
                         } else {
-                            // keep the numerators: 2^(y - mn) in (0, 1] as fp16 (2^-11 relative), with mn beside them
+                            // keep the numerators against the row's fixed reference: 2^(y - ref) = 2^(y - mn) * 2^(mn - ref)
+                            if (col0 == 0) ref = gm;                                   // maximum of the row's first 32 logits
                             uint32_t o[16];
+                            if (gm - ref <= 100.f) {
+                                // usual case: the stored value 2^(y - ref) also feeds the sum, rescaled once per group
+                                float accr = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                const float e0 = ptx::ex2_approx(y[i] - mn), e1 = ptx::ex2_approx(y[i + 1] - mn);
-                                acc += e0 + e1;
-                                o[i >> 1] = ptx::pack_f16x2(e0, e1);
+                                for (int i = 0; i < 32; i += 2) {
+                                    const float e0 = ptx::ex2_approx(y[i] - ref), e1 = ptx::ex2_approx(y[i + 1] - ref);
+                                    accr += e0 + e1;
+                                    o[i >> 1] = ptx::pack_bf16x2(e0, e1);
+                                }
+                                acc = accr * ptx::ex2_approx(ref - mn);
+                            } else {
+                                // a logit more than 2^100 above the reference (never seen outside adversarial inputs): the sum stays
+                                // exact against the running maximum, the stored values are clamped at 2^100
+#pragma unroll
+                                for (int i = 0; i < 32; i += 2) {
+                                    acc += ptx::ex2_approx(y[i] - mn) + ptx::ex2_approx(y[i + 1] - mn);
+                                    o[i >> 1] = ptx::pack_bf16x2(ptx::ex2_approx(fminf(y[i] - ref, 100.f)), ptx::ex2_approx(fminf(y[i + 1] - ref, 100.f)));
+                                }
                             }
                             __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
                             ptx::st_global_256(dst, o);
                             ptx::st_global_256(dst + 16, o + 8);
-                            p.gm[rowbase * (size_t)(p.V >> 5) + (size_t)(col0 >> 5) * 128 + r] = mn;   // [row block][group][row]: coalesced
                         }
                         s = s * ptx::ex2_approx(m2 - mn) + acc;
                         m2 = mn;
@@ -344,6 +360,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
             }
+            if (MODE == 2) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
             if (rv && p.lse) {   // (lse == NULL: a backward-time recompute that only wants the kept activations)
                 const float lse2 = m2 + log2f(s);
                 p.lse[cell] = lse2 * LN2;

@@ -8,7 +8,7 @@
 //                       (replaces gpu_rnnt_kernel.h:11-47, 79-113; arithmetic of cpu_rnnt.h:175-253)
 //   rnnt_grad_kernel    gradient w.r.t. logits (gpu_rnnt_kernel.h:143-179), padded cells zeroed
 //                       in the same pass (replaces the cudaMemsetAsync of gpu_rnnt.h:109)
-//   row_coef_kernel     per-row coefficients consumed by the prologues of the tensor-core backward GEMMs
+//   row_scale_kernel    per-row scales of the tensor-core backward GEMMs + the patch of the two special columns
 //   zgen/sgemm/...      fp32 building blocks of the exact (RNNTB200_FP32_EXACT) joint path
 //
 // Data layout ("skewed" planes): a per-utterance plane stores cell (t,u) at row n=t+u, column u:
@@ -16,6 +16,7 @@
 // so that step n of a wavefront touches ONE contiguous row (coalesced), which the reference's
 // (t*maxU+u) planes cannot offer (stride maxU-1 between neighbouring threads).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
@@ -357,47 +358,21 @@ __global__ void __launch_bounds__(256) rnnt_grad_kernel(const T* logits, T* out,
     }
 }
 
-// S = power of two with 128 <= S * max_b |g_b| < 256 (S = 1 when all g are 0 / not finite): the fp16 logit gradients of
-// the tensor-core backward are formed as S * dlogit, centred in the fp16 range whatever the caller's loss scaling;
-// out = {S, 1/S}.  One block.
-__global__ void __launch_bounds__(256) gscale_kernel(const float* __restrict__ g, int B, float* __restrict__ out) {
-    __shared__ float sm[256];
-    float m = 0.f;
-    for (int i = threadIdx.x; i < B; i += 256) m = fmaxf(m, fabsf(g[i]));
-    sm[threadIdx.x] = m;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (threadIdx.x < o) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + o]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        m = sm[0];
-        float S = 1.f;
-        if (m > 0.f && m < CUDART_INF_F) {
-            int e;
-            frexpf(m, &e);                       // m = f * 2^e, f in [0.5, 1)  ->  2^(e-1) <= m < 2^e
-            e = 8 - e;                           // S * m in [128, 256)
-            e = e > 100 ? 100 : (e < -100 ? -100 : e);
-            S = ldexpf(1.f, e);
-        }
-        out[0] = S; out[1] = 1.f / S;
-    }
-}
-
-// Per-ROW coefficients of the tensor-core backward, in the row order of the kept arrays (row = slot*128 + r, r = tl*8 + ul of
-// a 16 x 8 tile), so that the GEMM prologues fetch them with plain bulk copies:
-//   rowcoef[row] = (kd2, gS, dlbS, dllS):  S*dlogit[v] = gS * 2^(y_v + kd2)  for every v except the two special columns, whose
-//   final values S*dl_blank, S*dl_label are precomputed from the cached log-probs (the outgoing-arc terms of
-//   gpu_rnnt_kernel.h:163-172 subtracted);  kd2 = (alpha + beta - ll - lse) * log2(e);  rowlab[row] = label column or -1.
-// Rows outside the valid lattice get (-inf, 0, 0, 0), -1 and contribute exactly 0.
-__global__ void __launch_bounds__(256) row_coef_kernel(const int* __restrict__ tile_of_slot, const int* __restrict__ count, int b0,
-                                                       int nTb, int nUb, const int* __restrict__ xlen, const int* __restrict__ ylen,
-                                                       const int* __restrict__ labels, int blank, int maxT, int maxU, long long SK,
-                                                       const float* __restrict__ lse, const float* __restrict__ lpb,
-                                                       const float* __restrict__ lpl, const float* __restrict__ alphas,
-                                                       const float* __restrict__ betas, const float* __restrict__ llf,
-                                                       const float* __restrict__ gscale, const float* __restrict__ S2,
-                                                       float4* __restrict__ rowcoef, int* __restrict__ rowlab) {
+// Per-ROW scale of the tensor-core backward, in the row order of the kept arrays (row = slot*128 + r, r = tl*8 + ul of a
+// 16 x 8 tile), and the patch of the row's two special columns:
+//   dlogit[row, v] = g * exp(x_v + kd) = rs * E[row, v],   E = 2^(y_v - ref) kept by the forward (bf16),
+//   rs = g * 2^(ref + kd2),  kd2 = (alpha + beta - ll - lse) * log2(e)                       (gpu_rnnt_kernel.h:143-161)
+// except for v = blank and v = label_u, whose outgoing-arc terms (gpu_rnnt_kernel.h:163-172) are subtracted: their FINAL
+// values dl_blank, dl_label are formed here from the cached log-probs and stored as E' = dl / rs in place of E, so that
+// rs * E' is exact for them too.  Rows outside the valid lattice get rs = 0 (their E stays finite: it was formed from z = 0).
+__global__ void __launch_bounds__(256) row_scale_kernel(const int* __restrict__ tile_of_slot, const int* __restrict__ count, int b0,
+                                                        int nTb, int nUb, const int* __restrict__ xlen, const int* __restrict__ ylen,
+                                                        const int* __restrict__ labels, int blank, int maxT, int maxU, long long SK,
+                                                        const float* __restrict__ lse, const float* __restrict__ lpb,
+                                                        const float* __restrict__ lpl, const float* __restrict__ alphas,
+                                                        const float* __restrict__ betas, const float* __restrict__ llf,
+                                                        const float* __restrict__ gscale, const float* __restrict__ rowref, int V,
+                                                        unsigned short* __restrict__ E, float* __restrict__ rowscale) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int sl = (int)(row >> 7), r = (int)(row & 127);
     if (sl >= *count) return;
@@ -405,23 +380,29 @@ __global__ void __launch_bounds__(256) row_coef_kernel(const int* __restrict__ t
     const int bl = tile / per_utt, rem = tile - bl * per_utt, b = b0 + bl;
     const int t = (rem / nUb) * 16 + (r >> 3), u = (rem % nUb) * 8 + (r & 7);
     const int Tn = xlen[b], Un = ylen[b] + 1;
-    float4 o = make_float4(-CUDART_INF_F, 0.f, 0.f, 0.f);
-    int lab = -1;
+    float rs = 0.f;
     if (t < Tn && u < Un) {
         const long long k = sk_index(b, t, u, maxU, SK);
-        const float a = alphas[k], bt = betas[k], ll = llf[b], g = (gscale ? gscale[b] : 1.f) * S2[0];
+        const float a = alphas[k], bt = betas[k], ll = llf[b], g = gscale ? gscale[b] : 1.f;
         const float occ = a + bt - ll;                                   // log occupancy of the cell
         float sb = 0.f, sl_ = 0.f, pl = 0.f;
         if (t == Tn - 1 && u == Un - 1) sb = expf(a + lpb[k] - ll);
         if (t < Tn - 1) sb = expf(a + lpb[k] - ll + betas[k + maxU]);
         const bool has_label = u < Un - 1;
+        int lab = -1;
         if (has_label) { sl_ = expf(a + lpl[k] - ll + betas[k + maxU + 1]); pl = expf(lpl[k] + occ); lab = labels[(long long)b * (maxU - 1) + u]; }
         float dlb = g * (expf(lpb[k] + occ) - sb), dll = g * (pl - sl_);
         if (has_label && lab == blank) { dlb -= g * sl_; dll = dlb; }    // degenerate: label == blank
-        o = make_float4((occ - lse[((long long)b * maxT + t) * maxU + u]) * 1.4426950408889634f, g, dlb, dll);
+        rs = g * exp2f(rowref[row] + (occ - lse[((long long)b * maxT + t) * maxU + u]) * 1.4426950408889634f);
+        // cells whose whole gradient row is below 1e-30 contribute nothing: treating them as exactly 0 keeps 1/rs finite
+        // (a denormal rs would make it +inf and the patched columns NaN)
+        if (!(fabsf(rs) > 1e-30f && fabsf(rs) < CUDART_INF_F)) rs = 0.f;
+        const float inv = rs != 0.f ? 1.f / rs : 0.f;
+        unsigned short* e = E + row * (long long)V;
+        e[blank] = __bfloat16_as_ushort(__float2bfloat16(dlb * inv));
+        if (lab >= 0) e[lab] = __bfloat16_as_ushort(__float2bfloat16(dll * inv));
     }
-    rowcoef[row] = o;
-    rowlab[row] = lab;
+    rowscale[row] = rs;
 }
 
 // ---------------------------------------------------------------------------------------------

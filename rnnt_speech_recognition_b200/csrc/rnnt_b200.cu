@@ -151,7 +151,6 @@ rnntStatus_t compute_impl(const T* acts, T* grads, const int* labels, const int*
 // ------------------------------------------------------------------------------------------
 struct JointWs {
     LossWs<float> loss;
-    float* gscale;     // {S, 1/S}: power-of-two scale of the fp16 logit gradients (TC path)
     char* scratch;     // path-specific
     size_t scratch_bytes;
     long long chunk_rows;  // exact path
@@ -159,8 +158,6 @@ struct JointWs {
     JointWs(const rnntb200JointDesc& d, void* base) : loss(base, d.B, d.maxT, d.maxU) {
         const size_t N = (size_t)d.B * d.maxT * d.maxU;
         size_t off = align_up(loss.bytes, 256);
-        gscale = reinterpret_cast<float*>(static_cast<char*>(base) + off);
-        off += 256;
         scratch = static_cast<char*>(base) + off;
         if (d.precision == RNNTB200_FP32_EXACT) {
             const size_t per_row = (size_t)(2 * d.H + d.V) * sizeof(float);
@@ -407,7 +404,7 @@ rnntStatus_t rnntb200_joint_loss_backward(const rnntb200JointDesc* desc, const f
     unsigned nl = 0;
     const rb::LossPlanes lp{ws.loss.lse, ws.loss.lpb, ws.loss.lpl, ws.loss.alphas, ws.loss.betas, ws.loss.llf};
     rnntStatus_t st = rb::tc_backward(d, ws.scratch, enc, pred, bias, labels, label_lengths, input_lengths, lp, grad_costs,
-                                      ws.gscale, d_enc, d_pred, dW, db, s, &nl);
+                                      d_enc, d_pred, dW, db, s, &nl);
     RB_LAUNCHED(nl);
     return st;
 #else

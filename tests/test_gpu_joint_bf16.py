@@ -1,4 +1,4 @@
-"""Tensor-core path (tcgen05 fused joint kernels: fp16 forward projection, own dZ / dW gradient GEMMs) against the
+"""Tensor-core path (tcgen05 fused joint kernels: fp16 forward projection, own bf16 dZ / dW gradient GEMMs) against the
 fp64 oracle -- small shapes, BASELINE C2 at FULL size, and one full BASELINE C3 utterance -- and against the fp32 exact
 CUDA path.  16-bit operands carry 2^-12 (forward) / 2^-9 (gradient GEMMs) relative rounding, so this path is held to
 its own measured tolerance (DESIGN.md "Tolerances"), not to the fp32 rtol 1e-4 gate."""
@@ -16,7 +16,7 @@ from test_gpu_joint import run_joint, synth
 pytestmark = pytest.mark.gpu
 
 TC_COST_RTOL = 2e-4       # measured <= 4e-5 (profiles/r02/accuracy.json)
-TC_GRAD_NTOL = 5e-3       # norm-wise: |err| <= ntol * max|grad|; measured <= 2e-3
+TC_GRAD_NTOL = 1e-2       # element-wise: |err| <= ntol * max|grad| (bf16 gradient operands, 2^-9 each); Frobenius checks use 5e-3
 NAMES = ("d_enc", "d_pred", "dW", "db")
 
 

@@ -24,15 +24,13 @@ for _ in range(2):
 torch.cuda.synchronize()
 L = _lib.load()
 L.rnntb200_debug_prof.restype = C.POINTER(C.c_longlong)
-names = {0: ("bwd_dz_kernel", ["TMA: stage_empty", "MMA: priv_free / stage_full / a_ready / shared_free",
-                               "scaler: stage_full", "epilogue: acc_full / named barrier"]),
-         1: ("bwd_dw_kernel", ["TMA: stage_empty", "MMA: b_ready / a_ready", "scaler: named barrier / b_full",
-                               "producer: stage_empty / acc_full"])}
+names = {0: ("bwd_dz_kernel", ["TMA: stage_empty", "MMA: priv_free / stage_full / shared_free", "epilogue warp: acc_full / named barrier"]),
+         1: ("bwd_dw_kernel", ["TMA: stage_empty", "MMA: b_full / a_ready", "producer warp: b_full / acc_full"])}
 for which in (0, 1):
     ptr = L.rnntb200_debug_prof(which)
     a = np.ctypeslib.as_array(ptr, shape=(256, 4, 8)).copy()
     a = a[a[:, 1, 0] > 0]
     print(names[which][0], "CTAs", len(a))
-    for role in range(4):
+    for role in range(3):
         m = a[:, role, :5].mean(axis=0)
         print("  %-60s total %10.0f  waits %s" % (names[which][1][role], m[0], " ".join("%10.0f" % x for x in m[1:])))
