@@ -33,6 +33,7 @@ constexpr int DZ_STAGES = 3;
 constexpr int DW_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 z producers, then epilogue
 constexpr int DW_STAGES = 3;
 constexpr int DW_NV = 256;           // vocabulary columns per dW output tile
+constexpr int DW_NRS = 8;            // depth of the row-scale ring (K steps): the A producers run ahead of the B loads
 
 struct BwdParams {
     const float* enc; const float* pred;
@@ -373,13 +374,18 @@ __device__ __forceinline__ int dw_kind(const BwdParams& p, int item, int k2) {
 __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_constant__ CUtensorMap tmap_e, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    // stage = A: 2 x [128 x 64 k] K-major (32 KB) | B: 4 x [64 k x 64 v] MN-major (32 KB) | the 64 rows' scales (256 B, padded to 1 KB)
-    constexpr uint32_t STAGE = 65536u + 1024u, META = 65536u;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + DW_STAGES * STAGE);
-    uint64_t* b_full = bars;                       // [DW_STAGES] TMA -> producers, MMA
+    // stage = A: 2 x [128 x 64 k] K-major (32 KB) | B: 4 x [64 k x 64 v] MN-major (32 KB); beside the stages a ring of the
+    // K steps' row scales (64 floats each), loaded DW_NRS - DW_STAGES steps ahead of the B tiles so that the A producers
+    // only ever wait for the MMA to release a stage, never for a load
+    constexpr uint32_t STAGE = 65536u;
+    uint8_t* rsring = smem + DW_STAGES * STAGE;                 // [DW_NRS][64] floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rsring + DW_NRS * 256);
+    uint64_t* b_full = bars;                       // [DW_STAGES] TMA -> MMA
     uint64_t* a_ready = b_full + DW_STAGES;        // producers -> MMA
-    uint64_t* stage_empty = a_ready + DW_STAGES;   // MMA -> TMA
-    uint64_t* acc_full = stage_empty + DW_STAGES;
+    uint64_t* stage_empty = a_ready + DW_STAGES;   // MMA -> TMA, producers
+    uint64_t* rs_full = stage_empty + DW_STAGES;   // [DW_NRS] TMA -> producers
+    uint64_t* rs_empty = rs_full + DW_NRS;         // [DW_NRS] producers -> TMA
+    uint64_t* acc_full = rs_empty + DW_NRS;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -391,6 +397,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
         for (int i = 0; i < DW_STAGES; ++i) {
             ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&a_ready[i], narr ? narr : 1); ptx::mbar_init(&stage_empty[i], 1);
         }
+        for (int i = 0; i < DW_NRS; ++i) { ptx::mbar_init(&rs_full[i], 1); ptx::mbar_init(&rs_empty[i], narr ? narr : 1); }
         ptx::mbar_init(acc_full, 1);
         ptx::fence_barrier_init();
     }
@@ -416,15 +423,24 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
     const long long t_start = pf ? clock64() : 0;
 
     if (warp == 0) {
-        // ===================== TMA: B = kept numerators, boxes [64 rows x 64 v] (rows = K), + the rows' scales =====================
+        // ===================== TMA: B = kept numerators, boxes [64 rows x 64 v] (rows = K); the rows' scales run ahead =====================
         if (lane == 0) {
-            int stage = 0; uint32_t phase = 0;
+            const int nsteps = 2 * (s_end - s_beg);
+            auto load_rs = [&](int k) {        // K step k -> ring entry k % DW_NRS
+                const int e = k % DW_NRS;
+                ptx::mbar_wait(&rs_empty[e], ((k / DW_NRS) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&rs_full[e], 256u);
+                ptx::bulk_load_1d(rsring + e * 256, p.rowscale + (size_t)(s_beg + (k >> 1)) * 128 + (k & 1) * 64, 256u, &rs_full[e]);
+            };
+            if (narr)
+                for (int k = 0; k < DW_NRS - DW_STAGES && k < nsteps; ++k) load_rs(k);
+            int stage = 0; uint32_t phase = 0, it = 0;
             for (int s = s_beg; s < s_end; ++s)
-                for (int half = 0; half < 2; ++half) {
+                for (int half = 0; half < 2; ++half, ++it) {
+                    if (narr && (int)it + DW_NRS - DW_STAGES < nsteps) load_rs((int)it + DW_NRS - DW_STAGES);
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
-                    ptx::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)nbox * 8192u + 256u);
+                    ptx::mbar_arrive_expect_tx(&b_full[stage], (uint32_t)nbox * 8192u);
                     uint8_t* bs = smem + (size_t)stage * STAGE + 32768;
-                    ptx::bulk_load_1d(smem + (size_t)stage * STAGE + META, p.rowscale + (size_t)s * 128 + half * 64, 256u, &b_full[stage]);
                     for (int j = 0; j < nbox; ++j)
                         ptx::tma_load_2d(bs + j * 8192, &tmap_e, &b_full[stage], v0 + 64 * j, s * 128 + half * 64);
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
@@ -481,15 +497,16 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
             };
             load(tile_at(s_beg), pv, ev);
             int tile_n = tile_at(s_beg + 1);
-            int stage = 0; uint32_t phase = 0;
+            int stage = 0; uint32_t phase = 0, it = 0;
             for (int s = s_beg; s < s_end; ++s) {
                 const int tile_nn = tile_at(s + 2);
                 if (s + 1 < s_end) load(tile_n, npv, nev);
-                for (int half = 0; half < 2; ++half) {
-                    // b_full also says that the previous contents of the stage were consumed (the TMA waited for stage_empty)
-                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_full[stage], phase); RB_PROF_END(pf, pc[0]); }
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int e_rs = it % DW_NRS;
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }   // the MMAs that read this A slot retired
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&rs_full[e_rs], (it / DW_NRS) & 1); RB_PROF_END(pf, pc[2]); }
                     const uint32_t arow = smem_a + (uint32_t)stage * STAGE + (uint32_t)(k2 * 16384 + hl * 128);
-                    const uint32_t rsa = smem_a + (uint32_t)stage * STAGE + META;
+                    const uint32_t rsa = ptx::smem_u32(rsring) + (uint32_t)e_rs * 256u;
 #pragma unroll
                     for (int tl = 0; tl < 8; ++tl) {
                         const float e = half ? ev[8 + tl] : ev[tl];
@@ -504,7 +521,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                     }
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+                    if (lane == 0) { ptx::mbar_arrive(&a_ready[stage]); ptx::mbar_arrive(&rs_empty[e_rs]); }
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
                 }
                 tile_n = tile_nn;
@@ -515,16 +532,18 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
             }
         } else if (kind == 1 && hl < 32) {
             // SCALE block: one warp copies the stage's 64 row scales (bf16) into row 0 of the slot's A tile (row 0: no swizzle)
-            int stage = 0; uint32_t phase = 0;
+            int stage = 0; uint32_t phase = 0, it = 0;
             for (int s = s_beg; s < s_end; ++s)
-                for (int half = 0; half < 2; ++half) {
-                    ptx::mbar_wait(&b_full[stage], phase);
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int e_rs = it % DW_NRS;
+                    ptx::mbar_wait(&stage_empty[stage], phase ^ 1);
+                    ptx::mbar_wait(&rs_full[e_rs], (it / DW_NRS) & 1);
                     const uint32_t st = smem_a + (uint32_t)stage * STAGE;
-                    const float2 x = ptx::lds64f(st + META + (uint32_t)lane * 8u);
+                    const float2 x = ptx::lds64f(ptx::smem_u32(rsring) + (uint32_t)e_rs * 256u + (uint32_t)lane * 8u);
                     ptx::sts32(st + (uint32_t)(k2 * 16384) + (uint32_t)lane * 4u, ptx::pack_bf16x2(x.x, x.y));
                     ptx::fence_proxy_async_smem();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&a_ready[stage]);
+                    if (lane == 0) { ptx::mbar_arrive(&a_ready[stage]); ptx::mbar_arrive(&rs_empty[e_rs]); }
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
                 }
         }

@@ -76,7 +76,7 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
     g.priv = g.NCZ - g.sh;
     g.odd_base = 512 - g.priv;
     g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
-    g.dw_smem = 1024 + (size_t)3 * (65536 + 1024) + 512;
+    g.dw_smem = 1024 + (size_t)3 * 65536 + 8 * 256 + 512;
     g.nHB = (H + 127) / 128;
     g.nItems = (g.nHB + 2) / 2;               // blocks [0 .. nHB-1, ONES] in pairs
     g.nVT = (V + 255) / 256;

