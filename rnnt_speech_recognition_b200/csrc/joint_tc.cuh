@@ -345,6 +345,7 @@ inline bool tc_smem_optin(const void* func) {
 }  // namespace rb
 
 #include "joint_tc3.cuh"
+#include "joint_tc4.cuh"
 #include "bwd_tc.cuh"
 
 namespace rb {
@@ -379,6 +380,13 @@ inline bool tc_keep(const rnntb200JointDesc& d, const TcScratch& sc) {
     return d.keep_activations && env && sc.bchunk >= d.B;
 }
 
+// RNNTB200_FWD=3|4: forward kernel generation (4 = CTA pairs, the default; 3 = one CTA per tile, kept for A/B measurements)
+inline int tc_fwd_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_FWD"); v = e ? atoi(e) : 4; if (v != 3 && v != 4) v = 4; }
+    return v;
+}
+
 // the forward kernel over utterances [b0, b0+nb); KEEP: rank the chunk's valid tiles on the device (nothing is read
 // back) and leave numerators + maxima in the workspace
 template <bool KEEP>
@@ -386,7 +394,8 @@ inline rnntStatus_t tc_run_forward(const rnntb200JointDesc& d, const TcGeom& g, 
                                    const float* pred, const float* bias, const int* labels, const int* ylen,
                                    const int* xlen, float* lse, float* lpb, float* lpl, int b0, int nb, cudaStream_t s,
                                    unsigned* launches) {
-    const Tc2Geom g3 = tc3_geometry(d.H, d.V);
+    const bool pair = tc_fwd_variant() == 4;             // CTA-pair kernel (joint_tc4.cuh) or one CTA per tile (joint_tc3.cuh)
+    const Tc2Geom g3 = pair ? tc4_geometry(d.H, d.V) : tc3_geometry(d.H, d.V);
     JointTcParams p;
     tc_fill_params(d, g, p, enc, pred, bias, labels, ylen, xlen);
     p.b0 = b0; p.nb = nb;
@@ -400,13 +409,14 @@ inline rnntStatus_t tc_run_forward(const rnntb200JointDesc& d, const TcGeom& g, 
         p.slot = sc.slot; p.dl = sc.dl; p.gm = sc.gm;
     }
     CUtensorMap tm, tmp, tme;
-    if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, TC2_NC, g3.ks) ||
+    if (!make_tmap_bf16_kblocks(&tm, sc.Wt, d.V, d.H, pair ? TC2_NC / 2 : TC2_NC, g3.ks) ||
         !make_tmap_f32(&tmp, pred, (uint64_t)d.B * d.maxU, d.H, g.UU, 32, true) ||
         !make_tmap_f32(&tme, enc, (uint64_t)d.B * d.maxT, d.H, g.TT, 64, false)) {
         fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
         return RNNT_STATUS_EXECUTION_FAILED;
     }
     *launches += 1;
+    if (pair) return tc4_launch<KEEP ? 2 : 0>(g3, tm, tmp, tme, p, s);
     return tc3_launch<KEEP ? 2 : 0>(g3, tm, tmp, tme, p, s);
 }
 

@@ -1,79 +1,49 @@
-// joint_tc3.cuh -- the fused joint FORWARD kernel (model.py:158-166 + the log-softmax and
-// gather of gpu_rnnt.h:73-80 / gpu_rnnt_kernel.h:5-9), generation 3: the A operand z = tanh(enc + pred) lives in
-// TENSOR MEMORY as fp16, W^T (fp16) streams through a deep TMA ring, whole-stage MMA issue, TMA-fed producers.
-//
-// A dedicated warp TMA-loads the tile's pred rows (box [32 fp32 x UU rows], SWIZZLE_128B) and enc rows (box [64 x TT])
-// K block by K block into a ring, RUNNING AHEAD across tiles; each producer thread reads ITS OWN lattice row straight
-// from shared memory (conflict-free), applies tanh, packs to fp16 and writes its TMEM lane with tcgen05.st -- no
-// staging pass, no inter-warp barrier, no register prefetch buffers.
-//
-// Operand format: fp16 (same tcgen05.mma.kind::f16 rate as bf16, 11-bit instead of 8-bit significand): z is in
-// [-1, 1] and W ~ 1/sqrt(H), both far inside the fp16 range.  tanh is tanh.approx.f32 (2^-11 relative, one MUFU op);
-// the fp32-accurate form (ex2 + rcp, two MUFU ops: +0.45 ms per launch at C3 because z production is exposed once per
-// tile) changed neither the cost error (2.3e-5) nor the gradient error (2.9e-3) at C3 -- profiles/r02/accuracy.json.
-//
-// Roles (480 threads): warps 0-3 epilogue | 4-11 producers | 12 W TMA | 13 MMA | 14 enc/pred TMA
-//
-// MODE 0  forward: lse + (blank, label) log-probs per cell; nothing else leaves the SM
-// MODE 2  forward that KEEPS its activations (rnntb200JointDesc.keep_activations, and the backward's per-chunk
-//         recompute): MODE 0 + the softmax numerators E[row, v] = 2^(y_v - ref_row) as bf16, all columns of a row against
-//         ONE reference ref_row = the maximum of the row's first 32 logits (bf16 keeps its 8 significant bits over the whole
-//         exponent range, so any reference works; the exponent is clamped at +100), and ref_row itself.  The logit
-//         gradients are then row_scale * E: the two backward GEMMs take E straight from TMA and apply the row scale in an
-//         epilogue (dZ) or to the regenerated A operand (dW) -- no per-element prologue.
+// joint_tc4.cuh -- the fused joint forward kernel of joint_tc3.cuh as a CTA-PAIR kernel (thread-block cluster of 2,
+// tcgen05 cta_group::2).  Every 128-row tile re-reads all of W^T; with one CTA per tile that stream (22.5 GB of L2 -> SM
+// traffic per launch at C3) bounds the kernel.  Here two CTAs own two consecutive tiles and ONE copy of every W^T stage
+// between them:
+//   * W^T ring: each stage holds THIS CTA's 32 of the chunk's 64 vocabulary rows (4 KB per K block instead of 8); both
+//     halves complete on the LEADER's w_full (cp.async.bulk.tensor...cta_group::2, barrier addressed through mapa)
+//   * MMA: only the leader's warp 13 issues tcgen05.mma.cta_group::2 with M = 256 (128 TMEM lanes per CTA): A from each
+//     CTA's own z columns, B = the two shared-memory halves, D in the same accumulator columns of both CTAs
+//   * barriers: z_full (16 arrivals) and acc_empty (8) live in the leader and collect both CTAs (remote arrive through
+//     mapa); w_empty / acc_full / z_free are signalled in both CTAs by tcgen05.commit...multicast::cluster
+// Everything else -- input ring, producers, epilogues, TMEM budget -- is joint_tc3's code; a CTA whose tile lies outside the
+// valid lattice feeds zeros and keeps every handshake.  PTX forms validated by tools/probes/mma2_probe (profiles/r02).
 #pragma once
-#include <cuda_fp16.h>
-#include "joint_tc.cuh"
+#include "joint_tc3.cuh"
 
 namespace rb {
 
-constexpr int TC3_THREADS = 480;
-constexpr int TC3_IN_STAGES = 3;
-constexpr uint32_t TC3_PRED_BOX = 8 * 128, TC3_ENC_BOX = 16 * 256, TC3_IN_STAGE = 2 * TC3_PRED_BOX + TC3_ENC_BOX;   // 16 x 8 tiles
-constexpr int TC2_NC = 64;             // vocabulary columns per accumulator buffer / W^T chunk
-constexpr int TC2_MAX_STAGES = 24;
-constexpr int TC2_MAX_NBUF = 4;
-
-// z occupies H/2 TMEM columns (two fp16 per 32-bit column), the rest holds `nbuf` 64-column fp32 accumulators.
-// One W stage = ks K-blocks ([64 v x 64 k] boxes, 8 KB each): the MMA thread pays one mbarrier wait and one commit per
-// 4*ks MMAs (with ks = 1 the single issuing thread, not the tensor pipe, set the pace: 123 k cycles per tile measured).
-struct Tc2Geom { int nbuf, stages, zcols, ks; size_t smem_bytes; bool ok; };
-inline Tc2Geom tc3_geometry(int H, int V) {
-    Tc2Geom g{};
-    if (H % 64 || V % 64 || H < 64) return g;
-    g.zcols = (H / 64) * 32;
-    const int acc_cols = TC_TMEM_COLS - g.zcols;
-    g.nbuf = acc_cols / TC2_NC;
-    if (g.nbuf > TC2_MAX_NBUF) g.nbuf = TC2_MAX_NBUF;
-    if (g.nbuf < 2) return g;
-    const int KB = H / 64;
-    g.ks = 1;
-    for (int k = 5; k >= 1; --k)
-        if (KB % k == 0) { g.ks = k; break; }   // largest divisor of KB that is <= 5: stages are never partial
-    // smem: enc/pred ring (TC3_IN_STAGES x (2 x 1 KB pred boxes [32 fp32 x 8 rows] + 4 KB enc box [64 fp32 x 16 rows])) + W ring
+// W stages are half as large as joint_tc3's: twice as many fit
+inline Tc2Geom tc4_geometry(int H, int V) {
+    Tc2Geom g = tc3_geometry(H, V);
+    if (!g.ok) return g;
     const size_t in_bytes = (size_t)TC3_IN_STAGES * TC3_IN_STAGE;
     const size_t bias_bytes = V <= 4096 ? (size_t)V * 4 : 0;
     const size_t budget = 232448 - 1024 - 1024 - in_bytes - bias_bytes;
-    g.stages = (int)(budget / ((size_t)g.ks * 8192));
-    if (g.stages > 8) g.stages = 8;
-    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 8192 + 1024 + bias_bytes;
+    g.stages = (int)(budget / ((size_t)g.ks * 4096));
+    if (g.stages > 12) g.stages = 12;
+    g.smem_bytes = 1024 + in_bytes + (size_t)g.stages * g.ks * 4096 + 1024 + bias_bytes;
     g.ok = g.stages >= 2;
     return g;
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_constant__ CUtensorMap tmap_wt,
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) joint_tc4_kernel(const __grid_constant__ CUtensorMap tmap_wt,
                                                                    const __grid_constant__ CUtensorMap tmap_pred,
                                                                    const __grid_constant__ CUtensorMap tmap_enc,
                                                                    const JointTcParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int KB = p.KB, NCH = p.NCH, stages = p.stages, NBUF = p.nbuf, KS = p.ks;
-    const uint32_t stage_bytes = (uint32_t)KS * 8192u;
+    const uint32_t stage_bytes = (uint32_t)KS * 4096u;    // THIS CTA's half of a W stage: KS slabs of [32 v x 64 k]
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
     constexpr int NC = TC2_NC;
     uint8_t* insm = smem;                                 // TC3_IN_STAGES x {pred box k-half 0, k-half 1 (1 KB each, SW128), enc box (4 KB)}
     constexpr uint32_t IN_STAGE = TC3_IN_STAGE;
-    uint8_t* wsm = smem + TC3_IN_STAGES * IN_STAGE;       // stages x KS x [64 x 64] bf16, SW128 K-major (TMA)
+    uint8_t* wsm = smem + TC3_IN_STAGES * IN_STAGE;       // stages x KS x [32 x 64] fp16 (this CTA's vocabulary half), SW128 K-major (TMA)
     uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + (size_t)stages * stage_bytes);
     uint64_t* z_full = bars;                              // [TC_MAX_KB]      producers -> MMA (K block in TMEM)
     uint64_t* z_free = bars + TC_MAX_KB;                  //                  MMA -> producers
@@ -91,31 +61,44 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < TC_MAX_KB; ++i) ptx::mbar_init(&z_full[i], 8);
+        for (int i = 0; i < TC_MAX_KB; ++i) ptx::mbar_init(&z_full[i], 16);      // 8 producer warps of EACH CTA (the leader's copy is used)
         ptx::mbar_init(z_free, 1);
         for (int i = 0; i < TC2_MAX_STAGES; ++i) { ptx::mbar_init(&w_full[i], 1); ptx::mbar_init(&w_empty[i], 1); }
-        for (int i = 0; i < TC2_MAX_NBUF; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+        for (int i = 0; i < TC2_MAX_NBUF; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 8); }   // 4 epilogue warps of each CTA (leader's copy)
         for (int i = 0; i < TC3_IN_STAGES; ++i) { ptx::mbar_init(&in_full[i], 1); ptx::mbar_init(&in_empty[i], 8); }
         ptx::fence_barrier_init();
     }
-    if (warp == 13) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp == 13) { ptx::tmem_alloc2(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish2(); }   // the same warp of both CTAs
     if (warp == 12 && lane == 0) ptx::prefetch_tmap(&tmap_wt);
     if (warp == 14 && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
     ptx::tc_fence_before();
     __syncthreads();
+    ptx::cluster_sync();                                  // the peer's barriers exist before anyone arrives on them remotely
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t acc0 = tmem_base + (uint32_t)KB * 32;  // accumulator region starts after the z columns
-    const int ntiles = p.nb * p.nTb * p.nUb;
+    const int ntiles = p.nb * p.nTb * p.nUb, npairs = (ntiles + 1) >> 1, pstart = blockIdx.x >> 1, pstep = gridDim.x >> 1;
+    // The pair walks tile pairs (2q, 2q+1), one tile per CTA.  A CTA whose tile lies outside the valid lattice still takes
+    // part in every handshake of a live pair (z = 0, no input loads, no stores); a pair with two such tiles is skipped by all
+    // roles alike.
+    auto my_tile = [&](int q) { return 2 * q + (int)rank; };
+    auto tile_ok = [&](int t) { return t < ntiles && decode_tile(p, t).valid; };
+    auto pair_ok = [&](int q) { return tile_ok(2 * q) || tile_ok(2 * q + 1); };
+    // arrive on the LEADER's copy of a barrier (its count collects both CTAs)
+    auto arrive_leader = [&](uint64_t* bar) {
+        if (leader) ptx::mbar_arrive(bar);
+        else ptx::mbar_arrive_cluster(ptx::mapa_u32(bar, 0));
+    };
 
     if (warp == 14) {
         // ===================== enc / pred TMA: one K block of the tile's rows per ring stage, runs ahead across tiles
         if (lane == 0 && !(p.dbg & 8)) {
             int st = 0; uint32_t ph = 0;
             const uint32_t tx = 2u * (uint32_t)p.UU * 128u + (uint32_t)p.TT * 256u;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            for (int q = pstart; q < npairs; q += pstep) {
+                const int tile = my_tile(q);
+                if (!tile_ok(tile)) continue;            // nothing to load for a padding tile (or a dead pair)
                 const TileInfo ti = decode_tile(p, tile);
-                if (!ti.valid) continue;
                 for (int kb = 0; kb < KB; ++kb) {
                     ptx::mbar_wait(&in_empty[st], ph ^ 1);
                     ptx::mbar_arrive_expect_tx(&in_full[st], tx);
@@ -131,14 +114,16 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         // ===================== TMA producer =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-                if (!decode_tile(p, tile).valid) continue;
+            for (int q = pstart; q < npairs; q += pstep) {
+                if (!pair_ok(q)) continue;
                 if (p.dbg & 4) continue;
                 for (int c = 0; c < NCH; ++c)
                     for (int kb0 = 0; kb0 < KB; kb0 += KS) {   // KB % KS == 0: one 3-D box = KS K-block slabs
                         ptx::mbar_wait(&w_empty[stage], phase ^ 1);
-                        ptx::mbar_arrive_expect_tx(&w_full[stage], stage_bytes);
-                        ptx::tma_load_3d(wsm + (size_t)stage * stage_bytes, &tmap_wt, &w_full[stage], 0, c * NC, kb0);
+                        // both halves complete on the LEADER's barrier; only the leader posts the expected bytes
+                        if (leader) ptx::mbar_arrive_expect_tx(&w_full[stage], 2u * stage_bytes);
+                        ptx::tma_load_3d_2sm(wsm + (size_t)stage * stage_bytes, &tmap_wt, ptx::mapa_u32(&w_full[stage], 0), 0,
+                                             c * NC + 32 * (int)rank, kb0);
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                     }
             }
@@ -149,10 +134,11 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         // barrier addresses then stay in uniform registers.  (Issuing from inside `if (lane == 0)` made every
         // operand a vector register that had to be moved to the uniform datapath per instruction -- measured
         // 117 cycles per N=64 MMA instead of the 32-cycle dispatch floor.)
-        const uint32_t idesc = ptx::umma_idesc_f16(128, NC);
+        const uint32_t idesc = ptx::umma_idesc_f16(256, NC);   // M = 256: 128 lanes in each CTA of the pair
         int stage = 0; uint32_t phase = 0, g = 0, it = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            if (!decode_tile(p, tile).valid) continue;
+        if (leader)
+        for (int q = pstart; q < npairs; q += pstep) {
+            if (!pair_ok(q)) continue;
             for (int c = 0; c < NCH; ++c, ++g) {
                 const uint32_t buf = g % NBUF, use = g / NBUF;
                 if (!(p.dbg & 128)) {
@@ -176,7 +162,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                             if (ptx::elect_one()) {
 #pragma unroll
                                 for (int k = 0; k < 4; ++k)
-                                    ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8, bdesc0 + (uint64_t)(i * 512 + k * 2),
+                                    ptx::umma_ts2(d_tmem, a_st + i * 32 + k * 8, bdesc0 + (uint64_t)(i * 256 + k * 2),
                                                       idesc, (uint32_t)((kb0 | i | k) != 0));
                             }
                             __syncwarp();
@@ -191,27 +177,27 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                                 if (i < KS) {
 #pragma unroll
                                     for (int k = 0; k < 4; ++k)
-                                        ptx::umma_bf16_ts(d_tmem, a_st + i * 32 + k * 8,
-                                                          bdesc0 + (uint64_t)(i * 512 + k * 2), idesc,
+                                        ptx::umma_ts2(d_tmem, a_st + i * 32 + k * 8,
+                                                          bdesc0 + (uint64_t)(i * 256 + k * 2), idesc,
                                                           (i | k) ? 1u : (uint32_t)(kb0 != 0));
                                 }
                             }
-                            if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
-                            if (kb0 + KS >= KB) ptx::umma_commit(&acc_full[buf]);
+                            if (!(p.dbg & 4)) ptx::umma_commit2_mc(&w_empty[stage], 3);
+                            if (kb0 + KS >= KB) ptx::umma_commit2_mc(&acc_full[buf], 3);
                         }
                         __syncwarp();
                         if (++stage == stages) { stage = 0; phase ^= 1; }
                         continue;
                     }
                     if (ptx::elect_one()) {
-                        if (!(p.dbg & 4)) ptx::umma_commit(&w_empty[stage]);
-                        if (kb0 + KS >= KB) ptx::umma_commit(&acc_full[buf]);
+                        if (!(p.dbg & 4)) ptx::umma_commit2_mc(&w_empty[stage], 3);
+                        if (kb0 + KS >= KB) ptx::umma_commit2_mc(&acc_full[buf], 3);
                     }
                     __syncwarp();
                     if (++stage == stages) { stage = 0; phase ^= 1; }
                 }
             }
-            if (!(p.dbg & 8) && ptx::elect_one()) ptx::umma_commit(z_free);
+            if (!(p.dbg & 8) && ptx::elect_one()) ptx::umma_commit2_mc(z_free, 3);
             __syncwarp();
             ++it;
         }
@@ -222,10 +208,27 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         const bool fast_tanh = (p.dbg & 512) == 0;
         const uint32_t insm_a = ptx::smem_u32(insm);
         uint32_t it = 0; int st = 0; uint32_t ph = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const TileInfo ti = decode_tile(p, tile);
+        for (int q = pstart; q < npairs; q += pstep) {
             if (p.dbg & 8) continue;
-            if (!ti.valid) continue;
+            if (!pair_ok(q)) continue;
+            const int tile = my_tile(q);
+            if (!tile_ok(tile)) {
+                // the peer's tile is live: feed zeros for this CTA's half of the M = 256 instruction and keep every handshake
+                uint32_t zz[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) zz[i] = 0u;
+                for (int kb = 0; kb < KB; ++kb) {
+                    if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);
+                    ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zz);
+                    ptx::tmem_st_wait();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(&z_full[kb]);
+                }
+                ++it;
+                continue;
+            }
+            const TileInfo ti = decode_tile(p, tile);
             const int tl = r2 / p.UU, ul = r2 % p.UU;   // row of the enc box / of the pred box
             const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
             for (int kb = 0; kb < KB; ++kb) {
@@ -256,7 +259,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&z_full[kb]);
+                if (lane == 0) arrive_leader(&z_full[kb]);
             }
             ++it;
         }
@@ -265,9 +268,21 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const uint32_t bias_a = ptx::smem_u32(bias2);
         uint32_t g = 0;
-        for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int q = pstart; q < npairs; q += pstep) {
+            if (!pair_ok(q)) continue;
+            const int tile = my_tile(q);
+            if (!tile_ok(tile)) {                        // padding half of a live pair: release the accumulators, nothing else
+                for (int c = 0; c < NCH; ++c, ++g) {
+                    const uint32_t buf = g % NBUF, use = g / NBUF;
+                    ptx::mbar_wait(&acc_full[buf], use & 1);
+                    ptx::tc_fence_after();
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) arrive_leader(&acc_empty[buf]);
+                }
+                continue;
+            }
             const TileInfo ti = decode_tile(p, tile);
-            if (!ti.valid) continue;
             const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
             const int r = warp * 32 + lane;
             const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
@@ -357,7 +372,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
+                if (lane == 0) arrive_leader(&acc_empty[buf]);
             }
             if (MODE == 2) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
             if (rv && p.lse) {   // (lse == NULL: a backward-time recompute that only wants the kept activations)
@@ -371,18 +386,21 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 13) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    ptx::cluster_sync();                                  // the peer's barriers / tensor memory stay alive until both CTAs are done
+    if (warp == 13) ptx::tmem_dealloc2(tmem_base, TC_TMEM_COLS);
 }
 
 
+
 template <int MODE>
-inline rnntStatus_t tc3_launch(const Tc2Geom& g3, const CUtensorMap& tm, const CUtensorMap& tmp, const CUtensorMap& tme,
+inline rnntStatus_t tc4_launch(const Tc2Geom& g4, const CUtensorMap& tm, const CUtensorMap& tmp, const CUtensorMap& tme,
                                const JointTcParams& p, cudaStream_t s) {
-    if (!tc_smem_optin(reinterpret_cast<const void*>(joint_tc3_kernel<MODE>))) return RNNT_STATUS_EXECUTION_FAILED;
-    const int ntiles = p.nb * p.nTb * p.nUb;
-    const int grid = ntiles < tc_num_sms() ? ntiles : tc_num_sms();
-    ScopedTimer tmr(MODE == 0 ? "joint_tc3_kernel<fwd>" : "joint_tc3_kernel<fwd+keep>", s);
-    joint_tc3_kernel<MODE><<<grid, TC3_THREADS, g3.smem_bytes, s>>>(tm, tmp, tme, p);
+    if (!tc_smem_optin(reinterpret_cast<const void*>(joint_tc4_kernel<MODE>))) return RNNT_STATUS_EXECUTION_FAILED;
+    const int ntiles = p.nb * p.nTb * p.nUb, npairs = (ntiles + 1) / 2;
+    int grid = 2 * npairs < tc_num_sms() ? 2 * npairs : tc_num_sms();
+    grid &= ~1;
+    ScopedTimer tmr(MODE == 0 ? "joint_tc4_kernel<fwd>" : "joint_tc4_kernel<fwd+keep>", s);
+    joint_tc4_kernel<MODE><<<grid, TC3_THREADS, g4.smem_bytes, s>>>(tm, tmp, tme, p);
     return cudaGetLastError() == cudaSuccess ? RNNT_STATUS_SUCCESS : RNNT_STATUS_EXECUTION_FAILED;
 }
 

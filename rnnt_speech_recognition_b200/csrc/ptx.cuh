@@ -153,6 +153,58 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                  : "memory");
 }
 
+// ------------------------------------------------------------------ CTA pairs (cluster of 2, tcgen05 cta_group::2)
+// Validated on B200 by tools/probes/mma2_probe (profiles/r02/mma2_probe.log): exact accumulators in both CTAs, 32.1 cycles
+// per M=256 N=64 K=16 instruction.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `p` (a shared-memory object of THIS CTA's layout) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
+    return r;
+}
+// (default .release.cta semantics: what crosses the pair here are tcgen05 reads / writes, ordered by tcgen05.fence; a
+//  .release.cluster arrive costs a cluster-scope fence -- L1 invalidation -- on every handshake: measured +1.2 ms per launch)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMEM management for a CTA pair: the SAME warp of BOTH CTAs executes these
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[tmem of each CTA] . B[smem halves of both CTAs]^T, M = 256; issued by ONE thread of the leader CTA
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued cta_group::2 MMAs of this thread complete -> one arrive on the barrier at this offset in every CTA of the mask
+__device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"(cta_mask) : "memory");
+}
+// 3-D tiled load into THIS CTA's shared memory whose bytes are counted on an mbarrier given by its shared::cluster address
+// (the leader's barrier collects both halves of a pair's operand stage)
+__device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
 // ------------------------------------------------------------------ tcgen05: TMEM -> registers
 // 32 lanes x 32 consecutive 32-bit columns; thread i of the warp receives lane (base_lane + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

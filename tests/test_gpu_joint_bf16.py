@@ -144,14 +144,13 @@ def test_large_magnitude_logits(oracle):
 def test_kept_and_recomputed_backward_agree():
     """keep_activations: the backward consumes the numerators the forward call left in the workspace; without it the
     backward re-runs the same keeping forward itself, chunk by chunk.  Same kernels on the same data: identical costs
-    (both forward modes add the softmax terms in the same order) and gradients equal to fp32 round-off of the two
-    log-sum-exp formulations (the keeping mode sums 2^(y - ref), the plain one 2^(y - running max))."""
+    (both forward modes use the same arithmetic for the softmax sum) and gradients."""
     k = synth(6, 90, 50, 320, 256, 41, ragged=True)
     c1, g1 = run_joint(k, "bf16", keep=True)
     c2, g2 = run_joint(k, "bf16", keep=False)
-    assert_close(c1, c2, rtol=1e-6, atol=1e-5, what="costs")
+    assert np.array_equal(c1, c2)
     for a, b_, n in zip(g1, g2, NAMES):
-        assert_close(a, b_, rtol=0, atol=0, ntol=2e-4, what=n)
+        assert_close(a, b_, rtol=0, atol=0, ntol=1e-6, what=n)
 
 
 def test_backward_is_deterministic():
@@ -174,9 +173,11 @@ def test_multi_chunk_backward(tmp_path):
                        check=True, env=dict(os.environ, **env), timeout=300)
         outs.append(dict(np.load(f)))
     for o in outs[1:]:
-        assert_close(o["costs"], outs[0]["costs"], rtol=1e-6, atol=1e-5, what="costs")
-        for n in ("d_enc", "d_pred", "dW", "db"):               # (dW, db: summed over utterances in another order)
-            assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=2e-4, what=n)
+        assert np.array_equal(o["costs"], outs[0]["costs"])
+        for n in ("d_enc", "d_pred"):                           # per-utterance quantities
+            assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=1e-6, what=n)
+        for n in ("dW", "db"):                                  # summed over utterances in another order
+            assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=2e-5, what=n)
 
 
 def test_cuda_graph_capture_and_replay():
