@@ -28,8 +28,8 @@
 namespace rb {
 
 constexpr int BW_TT = 16, BW_UU = 8;
-constexpr int DZ_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 epilogue
-constexpr int DZ_STAGES = 3;
+constexpr int DZ_THREADS = 352;      // warp 0 operand TMA | 1 MMA | 2-9 epilogue | 10 enc/pred TMA for the epilogue
+constexpr int DZ_MAX_STAGES = 3;
 constexpr int DW_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 z producers, then epilogue
 constexpr int DW_STAGES = 3;
 constexpr int DW_NV = 256;           // vocabulary columns per dW output tile
@@ -46,6 +46,7 @@ struct BwdParams {
     const float* rowscale;      // per row of the kept arrays: rs_row (0 for rows outside the lattice)   [row_scale_kernel]
     // ---- dZ kernel
     int NP, NCZ, priv, sh, odd_base;   // passes over H, columns per pass, private / shared accumulator columns
+    int dz_stages;                     // operand ring depth (3, or 2 when the pass is too wide for three stages)
     float* d_enc;               // (B, maxT, H), rows of this launch's utterances are fully written
     float* ppred;               // (nTb, nb, maxU, H) partial planes of d_pred
     // ---- dW kernel
@@ -69,30 +70,41 @@ struct BwdParams {
 __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_constant__ CUtensorMap tmap_e,
                                                                const __grid_constant__ CUtensorMap tmap_wp,
                                                                const __grid_constant__ CUtensorMap tmap_ws,
+                                                               const __grid_constant__ CUtensorMap tmap_pred,
+                                                               const __grid_constant__ CUtensorMap tmap_enc,
                                                                const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NCZ = p.NCZ, NP = p.NP, priv = p.priv, sh = p.sh, KBV = p.V >> 6;
+    const int NCZ = p.NCZ, NP = p.NP, priv = p.priv, sh = p.sh, KBV = p.V >> 6, DZ_STAGES = p.dz_stages, nch = NCZ >> 5;
     const uint32_t stage_bytes = 16384u + (uint32_t)NCZ * 128u;            // A [128 rows x 64 v] | B [NCZ h x 64 v]
-    uint8_t* dpb = smem + (size_t)DZ_STAGES * stage_bytes;                 // [hh][buf][4][8][36] floats
+    // the unit's enc / pred rows for the epilogue's (1 - tanh^2): per 32-column chunk a pred box [32 fp32 x 8 rows] (1 KB,
+    // SWIZZLE_128B) and an enc box [32 fp32 x 16 rows] (2 KB), loaded by warp 10 while the unit's MMAs run (measured before:
+    // reading them with LDG put 54 % of the epilogue's stall samples on the L2 latency)
+    uint8_t* predb = smem + (size_t)DZ_STAGES * stage_bytes;               // [nch][8 x 128 B]
+    uint8_t* encb = predb + (size_t)nch * 1024;                            // [nch][16 x 128 B]
+    uint8_t* dpb = encb + (size_t)nch * 2048;                              // [hh][buf][4][8][36] floats
     constexpr int DP_ONE = 4 * 8 * 36;                                     // floats per (hh, buf)
     uint64_t* bars = reinterpret_cast<uint64_t*>(dpb + 2 * 2 * DP_ONE * 4);
-    uint64_t* stage_full = bars;                     // [DZ_STAGES] TMA -> MMA
-    uint64_t* stage_empty = stage_full + DZ_STAGES;  // [DZ_STAGES] MMA -> TMA
-    uint64_t* acc_full = stage_empty + DZ_STAGES;    // [2] MMA -> epilogue (unit parity)
-    uint64_t* priv_free = acc_full + 2;              // [2] epilogue -> MMA
-    uint64_t* shared_free = priv_free + 2;           // [1]
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(shared_free + 1);
+    uint64_t* stage_full = bars;                         // [stages] TMA -> MMA
+    uint64_t* stage_empty = stage_full + DZ_MAX_STAGES;  // [stages] MMA -> TMA
+    uint64_t* acc_full = stage_empty + DZ_MAX_STAGES;    // [2] MMA -> epilogue (unit parity)
+    uint64_t* priv_free = acc_full + 2;                  // [2] epilogue -> MMA
+    uint64_t* shared_free = priv_free + 2;               // [1]
+    uint64_t* epi_full = shared_free + 1;                // enc/pred TMA -> epilogue
+    uint64_t* epi_empty = epi_full + 1;                  // epilogue -> enc/pred TMA
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(epi_empty + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int i = 0; i < DZ_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&stage_empty[i], 1); }
+        for (int i = 0; i < DZ_MAX_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&stage_empty[i], 1); }
+        ptx::mbar_init(epi_full, 1); ptx::mbar_init(epi_empty, 8);
         for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], 8); }
         ptx::mbar_init(shared_free, 8);
         ptx::fence_barrier_init();
     }
     if (warp == 1) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_e); ptx::prefetch_tmap(&tmap_wp); ptx::prefetch_tmap(&tmap_ws); }
+    if (warp == 10 && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -178,6 +190,26 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     }
                 }
         }
+    } else if (warp == 10) {
+        // ===================== enc / pred TMA for the epilogue: one unit ahead of it =====================
+        if (lane == 0) {
+            uint32_t uq = 0;
+            for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+                const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
+                const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
+                if (tb * BW_TT >= Tn) continue;
+                const int nub = (Un + BW_UU - 1) / BW_UU;
+                for (int ub = 0; ub < nub; ++ub)
+                    for (int pass = 0; pass < NP; ++pass, ++uq) {
+                        ptx::mbar_wait(epi_empty, (uq & 1) ^ 1);
+                        ptx::mbar_arrive_expect_tx(epi_full, (uint32_t)nch * 3072u);
+                        for (int c = 0; c < nch; ++c) {
+                            ptx::tma_load_2d(predb + c * 1024, &tmap_pred, epi_full, pass * NCZ + 32 * c, b * p.maxU + ub * BW_UU);
+                            ptx::tma_load_2d(encb + c * 2048, &tmap_enc, epi_full, pass * NCZ + 32 * c, b * p.maxT + tb * BW_TT);
+                        }
+                    }
+            }
+        }
     } else {
         // ===================== epilogue (warps 2-9): g = rs_row * acc * (1 - tanh^2), tile sums =====================
         const int qd = warp & 3, hh = (warp - 2) >> 2, qslot = (warp - 2) & 3;
@@ -188,6 +220,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         const uint32_t dp0 = ptx::smem_u32(dpb) + (uint32_t)hh * 2 * DP_ONE * 4;
         const int off4 = (ul & 1) * 16 + ((ul >> 1) & 1) * 8 + ((ul >> 2) & 1) * 4;   // columns this lane keeps after the u butterfly
         const int cbase = ((lane >> 3) & 1) * 16 + ((lane >> 4) & 1) * 8;              // ... after the t butterfly
+        const uint32_t enc_a = ptx::smem_u32(encb) + (uint32_t)(r >> 3) * 128u, pred_a = ptx::smem_u32(predb) + (uint32_t)ul * 128u;
         uint32_t q = 0, nchunk = 0;
         for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
             const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
@@ -195,7 +228,6 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
             if (tb * BW_TT >= Tn) continue;
             const int nub = (Un + BW_UU - 1) / BW_UU;
             const int t = tb * BW_TT + (r >> 3);
-            const float* erow = p.enc + ((size_t)b * p.maxT + min(t, p.maxT - 1)) * p.H;
             float accE[2][6][4];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
@@ -204,8 +236,6 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
 #pragma unroll
                     for (int i = 0; i < 4; ++i) accE[a][j][i] = 0.f;
             for (int ub = 0; ub < nub; ++ub) {
-                const int u = ub * BW_UU + ul;
-                const float* prow = p.pred + ((size_t)b * p.maxU + min(u, p.maxU - 1)) * p.H;
                 const int tile = (bl * p.nTb + tb) * p.nUb + ub;
                 const float rs = __ldg(p.rowscale + (size_t)(p.slot ? p.slot[tile] : tile) * 128 + r);   // 0 outside the lattice
 #pragma unroll
@@ -214,6 +244,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     const uint32_t par = q & 1;
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&acc_full[par], (q >> 1) & 1); RB_PROF_END(pf, pc[0]); }
                     ptx::tc_fence_after();
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(epi_full, q & 1); RB_PROF_END(pf, pc[2]); }
                     const int n0 = pass * NCZ;
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
@@ -234,11 +265,10 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                         const int h0 = n0 + 32 * c;
                         float g[32];
                         {
-                            const float4* e4 = reinterpret_cast<const float4*>(erow + h0);
-                            const float4* q4 = reinterpret_cast<const float4*>(prow + h0);
 #pragma unroll
                             for (int i = 0; i < 8; ++i) {
-                                const float4 e = __ldg(e4 + i), qq = __ldg(q4 + i);
+                                const float4 e = ptx::lds128f(enc_a + (uint32_t)(c * 2048 + i * 16)),
+                                             qq = ptx::lds128f(pred_a + (uint32_t)(c * 1024 + ((i ^ (ul & 7)) << 4)));
                                 const float z0 = ptx::tanh_approx(e.x + qq.x), z1 = ptx::tanh_approx(e.y + qq.y),
                                             z2 = ptx::tanh_approx(e.z + qq.z), z3 = ptx::tanh_approx(e.w + qq.w);
                                 const float d0 = __uint_as_float(v[4 * i]) * rs, d1 = __uint_as_float(v[4 * i + 1]) * rs,
@@ -299,6 +329,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                             ++nchunk;
                         }
                     }
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(epi_empty);      // this warp has read the unit's enc / pred rows
                     ++q;
                 }
             }

@@ -61,7 +61,7 @@ inline int tc_num_sms() {
 //   dW: output tiles of (2 block slots of 128 rows out of [H blocks..., ONES]) x 256 columns of V, split S ways over the
 //       lattice rows.
 struct BwdGeom {
-    int NP, NCZ, priv, sh, odd_base;
+    int NP, NCZ, priv, sh, odd_base, dz_stages;
     size_t dz_smem, dw_smem;
     int nVT, nHB, nItems, S_max, dw_grid;     // S_max = the split count S
     bool ok;
@@ -75,7 +75,10 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
     g.sh = 2 * g.NCZ > 512 ? 2 * g.NCZ - 512 : 0;
     g.priv = g.NCZ - g.sh;
     g.odd_base = 512 - g.priv;
-    g.dz_smem = 1024 + (size_t)3 * (16384 + (size_t)g.NCZ * 128) + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+    for (g.dz_stages = 3; g.dz_stages >= 2; --g.dz_stages) {
+        g.dz_smem = 1024 + (size_t)g.dz_stages * (16384 + (size_t)g.NCZ * 128) + (size_t)(g.NCZ / 32) * 3072 + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+        if (g.dz_smem <= 232448) break;
+    }
     g.dw_smem = 1024 + (size_t)3 * 65536 + 8 * 256 + 512;
     g.nHB = (H + 127) / 128;
     g.nItems = (g.nHB + 2) / 2;               // blocks [0 .. nHB-1, ONES] in pairs
@@ -454,8 +457,10 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
         return RNNT_STATUS_MEMOPS_FAILED;
-    CUtensorMap tm_e128, tm_e64, tm_wp, tm_ws;
-    if (!make_tmap_bf16(&tm_e128, sc.dl, sc.rows_chunk, d.V, 128) || !make_tmap_bf16(&tm_e64, sc.dl, sc.rows_chunk, d.V, 64) ||
+    CUtensorMap tm_e128, tm_e64, tm_wp, tm_ws, tm_p32, tm_e32;
+    if (!make_tmap_f32(&tm_p32, pred, (uint64_t)d.B * d.maxU, d.H, BW_UU, 32, true) ||
+        !make_tmap_f32(&tm_e32, enc, (uint64_t)d.B * d.maxT, d.H, BW_TT, 32, false) ||
+        !make_tmap_bf16(&tm_e128, sc.dl, sc.rows_chunk, d.V, 128) || !make_tmap_bf16(&tm_e64, sc.dl, sc.rows_chunk, d.V, 64) ||
         !make_tmap_bf16(&tm_wp, sc.Wb, d.H, d.V, bg.priv) || !make_tmap_bf16(&tm_ws, sc.Wb, d.H, d.V, bg.sh ? bg.sh : 8)) {
         fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
         return RNNT_STATUS_EXECUTION_FAILED;
@@ -480,7 +485,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             *launches += 1;
         }
         p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.rowscale = sc.rowscale;
-        p.NP = bg.NP; p.NCZ = bg.NCZ; p.priv = bg.priv; p.sh = bg.sh; p.odd_base = bg.odd_base;
+        p.NP = bg.NP; p.NCZ = bg.NCZ; p.priv = bg.priv; p.sh = bg.sh; p.odd_base = bg.odd_base; p.dz_stages = bg.dz_stages;
         p.d_enc = d_enc; p.ppred = sc.ppl;
         p.nVT = bg.nVT; p.nItems = bg.nItems; p.nHB = bg.nHB; p.S = bg.S_max; p.Hrows = d.H;
         p.dWp = sc.dWp; p.dbp = sc.dbp;
@@ -492,7 +497,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             const int nruns = nb * g.nTb;
             ScopedTimer tmr("bwd_dz_kernel", s);
             p.prof = prof_dz;
-            bwd_dz_kernel<<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, p);
+            bwd_dz_kernel<<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
         }
         {
             const size_t n4 = (size_t)nb * d.maxU * d.H / 4;
