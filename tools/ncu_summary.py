@@ -47,6 +47,8 @@ def traffic(res, steps):
     for key, d in res.items():
         name = key.split(" #")[0]
         short = name.split("(")[0].replace("rb::", "").replace("void ", "").strip()
+        # the names bench.py's CUDA-event attribution uses for the two template instances of the forward kernel
+        short = short.replace("_kernel<2>", "_kernel<fwd+keep>").replace("_kernel<0>", "_kernel<fwd>")
         def num(k):
             v = d.get(k, "0").split()
             x = float(v[0].replace(",", "")) if v else 0.0
