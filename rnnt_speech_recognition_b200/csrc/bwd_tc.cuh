@@ -30,7 +30,7 @@ namespace rb {
 constexpr int BW_TT = 16, BW_UU = 8;
 constexpr int DZ_THREADS = 352;      // warp 0 operand TMA | 1 MMA | 2-9 epilogue | 10 enc/pred TMA for the epilogue
 constexpr int DZ_MAX_STAGES = 3;
-constexpr int DW_THREADS = 320;      // warp 0 TMA | 1 MMA | 2-9 z producers, then epilogue
+constexpr int DW_THREADS = 576;      // warp 0 TMA | 1 MMA | 2-17 z producers, then epilogue (16 warps: the tanh chain is latency-bound at 2 warps per scheduler)
 constexpr int DW_STAGES = 3;
 constexpr int DW_NV = 256;           // vocabulary columns per dW output tile
 constexpr int DW_NRS = 8;            // depth of the row-scale ring (K steps): the A producers run ahead of the B loads
@@ -42,6 +42,7 @@ struct BwdParams {
     int nTb, nUb, b0, nb;
     const int* slot;            // tile -> row block of the kept arrays (-1: tile outside the valid lattice)
     const int* tile_of_slot;    // inverse map (valid tiles only)
+    const int4* slot_meta;      // per compact slot {first enc row, first pred row, #t rows, #u rows} of the tile
     const int* count;           // number of valid tiles (device word)
     const float* rowscale;      // per row of the kept arrays: rs_row (0 for rows outside the lattice)   [row_scale_kernel]
     // ---- dZ kernel
@@ -67,6 +68,7 @@ struct BwdParams {
 // valid tiles along u; inside a tile NP passes over H.  Accumulators: an even unit uses TMEM columns [0, NCZ), an odd
 // unit [priv .. NCZ) (the SHARED zone, drained first by the epilogue) + [odd_base, 512): two units are in flight
 // (MMA of unit q+1 over the epilogue of unit q) although 2*NCZ may exceed the 512 columns.
+template <bool PROF>
 __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_constant__ CUtensorMap tmap_e,
                                                                const __grid_constant__ CUtensorMap tmap_wp,
                                                                const __grid_constant__ CUtensorMap tmap_ws,
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int nruns = p.nb * p.nTb;
-    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);
+    const bool pf = PROF && p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);   // PROF = false: all of it folds away
     long long pc[4] = {0, 0, 0, 0};
     const long long t_start = pf ? clock64() : 0;
 
@@ -403,6 +405,7 @@ __device__ __forceinline__ int dw_kind(const BwdParams& p, int item, int k2) {
     return blk < p.nHB ? 0 : (blk == p.nHB ? 1 : 2);
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_constant__ CUtensorMap tmap_e, const BwdParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -424,7 +427,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
     const DwWork wk = dw_decode(p, blockIdx.x);
     const int v0 = wk.vt * DW_NV, Nv = min(DW_NV, p.V - v0), nbox = Nv >> 6;
     const int kind0 = dw_kind(p, wk.item, 0), kind1 = dw_kind(p, wk.item, 1);
-    const int narr = 4 * ((kind0 == 0) + (kind1 == 0)) + (kind0 == 1) + (kind1 == 1);   // warps that arrive on a_ready per K step
+    const int narr = 8 * ((kind0 == 0) + (kind1 == 0)) + (kind0 == 1) + (kind1 == 1);   // warps that arrive on a_ready per K step
     if (threadIdx.x == 0) {
         for (int i = 0; i < DW_STAGES; ++i) {
             ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&a_ready[i], narr ? narr : 1); ptx::mbar_init(&stage_empty[i], 1);
@@ -450,7 +453,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
     const long long cnt = *p.count;
     const int s_beg = (int)(cnt * wk.split / p.S), s_end = (int)(cnt * (wk.split + 1) / p.S);
     const int per_utt = p.nTb * p.nUb;
-    const bool pf = p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);
+    const bool pf = PROF && p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);   // PROF = false: all of it folds away
     long long pc[4] = {0, 0, 0, 0};
     const long long t_start = pf ? clock64() : 0;
 
@@ -507,32 +510,36 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                 if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
             }
     } else {
-        // ===================== A producers (warps 2-9): thread = column h of the joint (or the SCALE row); then the epilogue =====================
-        const int ptid = threadIdx.x - 64, k2 = ptid >> 7, hl = ptid & 127;
+        // ===================== A producers (warps 2-17): thread = (column h of the joint, 4 of a K step's 8 time rows), or the SCALE row; then the epilogue =====================
+        const int ptid = threadIdx.x - 64, k2 = ptid >> 8, q2 = (ptid >> 7) & 1, hl = ptid & 127;
         const int kind = k2 ? kind1 : kind0, hb = 2 * wk.item + k2;
         const int h = hb * 128 + hl;
-        const bool hv = kind == 0 && h < p.H;
         const uint32_t smem_a = ptx::smem_u32(smem);
         if (kind == 0) {
-            // Inputs of slot s+1 (its tile's 8 pred rows and 16 enc rows of this thread's column h) are loaded while slot s is
-            // computed; the tile id is read two slots ahead, so no load waits on another load.  Rows outside the lattice
-            // carry rs = 0, so no length test is needed here.
-            auto tile_at = [&](int s) { return s < s_end ? (p.tile_of_slot ? p.tile_of_slot[s] : s) : 0; };
-            float pv[8], ev[16], npv[8], nev[16];
-            auto load = [&](int tile, float* pvv, float* evv) {
-                const int bl = tile / per_utt, rem = tile - bl * per_utt, b = p.b0 + bl;
-                const int t0 = (rem / p.nUb) * BW_TT, u0 = (rem % p.nUb) * BW_UU;
+            // Inputs of slot s+1 (its tile's 8 pred rows and this thread's 8 enc rows of column h) are loaded while slot s is
+            // computed; the slot's descriptor is read two slots ahead, so no load waits on another load.  No division and no
+            // 64-bit multiply per load: the descriptor carries the tile's first rows (measured: with the tile decoded here and
+            // the rows addressed one by one, two thirds of the producers' instructions were integer address arithmetic and the
+            // kernel was issue-bound).  Rows outside the lattice carry rs = 0, so no length test is needed, only in-bounds reads.
+            const int hc = min(h, p.H - 1);     // columns past H (H % 128 != 0) feed output rows nobody reads
+            auto meta_at = [&](int s) { return s < s_end ? __ldg(p.slot_meta + s) : make_int4(0, 0, 1, 1); };
+            float pv[8], ev[8], npv[8], nev[8];     // ev[half * 4 + j] = enc row t0 + half * 8 + q2 * 4 + j
+            auto load = [&](const int4 m, float* pvv, float* evv) {
+                const char* pp = reinterpret_cast<const char*>(p.pred + (size_t)m.y * p.H + hc);
+                const char* pe = reinterpret_cast<const char*>(p.enc + (size_t)m.x * p.H + hc);
+                const uint32_t hb4 = (uint32_t)p.H * 4u;      // unsigned 32-bit byte offsets inside the tile: one IMAD.WIDE.U32 per address
 #pragma unroll
-                for (int k = 0; k < 8; ++k) pvv[k] = hv ? __ldg(p.pred + ((size_t)b * p.maxU + min(u0 + k, p.maxU - 1)) * p.H + h) : 0.f;
+                for (int k = 0; k < 8; ++k) pvv[k] = __ldg(reinterpret_cast<const float*>(pp + (uint32_t)min(k, m.w - 1) * hb4));
 #pragma unroll
-                for (int k = 0; k < 16; ++k) evv[k] = hv ? __ldg(p.enc + ((size_t)b * p.maxT + min(t0 + k, p.maxT - 1)) * p.H + h) : 0.f;
+                for (int k = 0; k < 8; ++k)
+                    evv[k] = __ldg(reinterpret_cast<const float*>(pe + (uint32_t)min((k >> 2) * 8 + q2 * 4 + (k & 3), m.z - 1) * hb4));
             };
-            load(tile_at(s_beg), pv, ev);
-            int tile_n = tile_at(s_beg + 1);
+            load(meta_at(s_beg), pv, ev);
+            int4 meta_n = meta_at(s_beg + 1);
             int stage = 0; uint32_t phase = 0, it = 0;
             for (int s = s_beg; s < s_end; ++s) {
-                const int tile_nn = tile_at(s + 2);
-                if (s + 1 < s_end) load(tile_n, npv, nev);
+                const int4 meta_nn = meta_at(s + 2);
+                if (s + 1 < s_end) load(meta_n, npv, nev);
                 for (int half = 0; half < 2; ++half, ++it) {
                     const int e_rs = it % DW_NRS;
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }   // the MMAs that read this A slot retired
@@ -540,8 +547,9 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                     const uint32_t arow = smem_a + (uint32_t)stage * STAGE + (uint32_t)(k2 * 16384 + hl * 128);
                     const uint32_t rsa = ptx::smem_u32(rsring) + (uint32_t)e_rs * 256u;
 #pragma unroll
-                    for (int tl = 0; tl < 8; ++tl) {
-                        const float e = half ? ev[8 + tl] : ev[tl];
+                    for (int j = 0; j < 4; ++j) {
+                        const int tl = q2 * 4 + j;
+                        const float e = half ? ev[4 + j] : ev[j];
                         const float4 r0 = ptx::lds128f(rsa + (uint32_t)(tl * 32)), r1 = ptx::lds128f(rsa + (uint32_t)(tl * 32 + 16));   // rs of rows tl*8 .. +7
                         const float rsv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
                         float z[8];
@@ -556,13 +564,13 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
                     if (lane == 0) { ptx::mbar_arrive(&a_ready[stage]); ptx::mbar_arrive(&rs_empty[e_rs]); }
                     if (++stage == DW_STAGES) { stage = 0; phase ^= 1; }
                 }
-                tile_n = tile_nn;
+                meta_n = meta_nn;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) pv[k] = npv[k];
 #pragma unroll
-                for (int k = 0; k < 16; ++k) ev[k] = nev[k];
+                for (int k = 0; k < 8; ++k) ev[k] = nev[k];
             }
-        } else if (kind == 1 && hl < 32) {
+        } else if (kind == 1 && (ptid & 255) < 32) {
             // SCALE block: one warp copies the stage's 64 row scales (bf16) into row 0 of the slot's A tile (row 0: no swizzle)
             int stage = 0; uint32_t phase = 0, it = 0;
             for (int s = s_beg; s < s_end; ++s)
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
             const bool on = kind == 0 ? hr < p.Hrows : (qd == 0 && lane == 0);
             float* dst = kind == 0 ? p.dWp + ((size_t)wk.split * p.Hrows + hr) * p.V + v0 : p.dbp + (size_t)wk.split * p.V + v0;
             if (kind == 0 || qd == 0) {
-                for (int j = 0; j < (Nv >> 5); ++j) {
+                for (int j = q2 * (Nv >> 6); j < (q2 + 1) * (Nv >> 6); ++j) {     // the slot's two warps per lane quarter take half the columns each
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(k2 * DW_NV + j * 32), v);
                     ptx::tmem_ld_wait();

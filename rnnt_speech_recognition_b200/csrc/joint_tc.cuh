@@ -143,7 +143,8 @@ __global__ void __launch_bounds__(256) convert_w_kernel(const float* __restrict_
 __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restrict__ xlen, const int* __restrict__ ylen,
                                                             int b0, int ntiles, int nTb, int nUb, int TT, int UU,
                                                             int* __restrict__ slot, int* __restrict__ count,
-                                                            int* __restrict__ tile_of_slot = nullptr) {
+                                                            int* __restrict__ tile_of_slot = nullptr,
+                                                            int4* __restrict__ slot_meta = nullptr, int maxT = 0, int maxU = 0) {
     __shared__ int warp_sums[32];
     __shared__ int base;
     if (threadIdx.x == 0) base = 0;
@@ -152,9 +153,14 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restric
     for (int t0 = 0; t0 < ntiles; t0 += 1024) {
         const int tile = t0 + threadIdx.x;
         int v = 0;
+        int4 meta = make_int4(0, 0, 1, 1);
         if (tile < ntiles) {
             const int bl = tile / per_utt, rem = tile - bl * per_utt, b = b0 + bl;
-            v = ((rem / nUb) * TT < xlen[b] && (rem % nUb) * UU < ylen[b] + 1) ? 1 : 0;
+            const int tt = (rem / nUb) * TT, uu = (rem % nUb) * UU;
+            v = (tt < xlen[b] && uu < ylen[b] + 1) ? 1 : 0;
+            // what the kernels that walk the compact slots need of a tile, so that none of them divides: first enc / pred row
+            // (in rows of H floats) and how many of the tile's TT / UU rows exist in the padded arrays
+            meta = make_int4(b * maxT + tt, b * maxU + uu, min(TT, maxT - tt), min(UU, maxU - uu));
         }
         int incl = v;
 #pragma unroll
@@ -172,6 +178,7 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restric
         if (tile < ntiles) {
             slot[tile] = v ? excl : -1;
             if (v && tile_of_slot) tile_of_slot[excl] = tile;
+            if (v && slot_meta) slot_meta[excl] = meta;
         }
         __syncthreads();
         if (threadIdx.x == 1023) base = excl + v;
@@ -260,6 +267,7 @@ struct TcScratch {
     float* gm;                              // (rows_chunk) fp32 reference of each row's numerators (log2 domain)
     int* slot;                              // tile -> compact row block (-1: outside the valid lattice), per chunk
     int* tile_of_slot;                      // compact row block -> tile
+    int4* slot_meta;                        // compact row block -> {first enc row, first pred row, #t rows, #u rows} (tile_compact_kernel)
     int* count;                             // number of valid tiles of the chunk
     float* ppl;                             // (nTb, bchunk, maxU, H) fp32 partial planes of d_pred (bwd_dz_kernel)
     float* dWp;                             // (S_max, H, V) fp32 split-K planes of dW (bwd_dw_kernel)
@@ -295,6 +303,7 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     s.gm = reinterpret_cast<float*>(take(s.rows_chunk * 4));
     s.slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
     s.tile_of_slot = reinterpret_cast<int*>(take((size_t)bc * g.nTb * g.nUb * 4));
+    s.slot_meta = reinterpret_cast<int4*>(take((size_t)bc * g.nTb * g.nUb * 16));
     s.count = reinterpret_cast<int*>(take(256));
     s.ppl = reinterpret_cast<float*>(take((size_t)g.nTb * bc * d.maxU * d.H * 4));
     s.dWp = reinterpret_cast<float*>(take((size_t)bg.S_max * d.H * d.V * 4));
@@ -407,7 +416,8 @@ inline rnntStatus_t tc_run_forward(const rnntb200JointDesc& d, const TcGeom& g, 
     p.dbg = tc_dbg();
     if (KEEP) {
         const int ntiles = nb * g.nTb * g.nUb;
-        tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count, sc.tile_of_slot);
+        tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count, sc.tile_of_slot, sc.slot_meta,
+                                             d.maxT, d.maxU);
         *launches += 1;
         p.slot = sc.slot; p.dl = sc.dl; p.gm = sc.gm;
     }
@@ -452,7 +462,8 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     const BwdGeom bg = bwd_geometry(d.H, d.V);
     TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
     const bool kept = tc_keep(d, sc);
-    if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel)))
+    if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<false>)) ||
+        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<true>)))
         return RNNT_STATUS_EXECUTION_FAILED;
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
@@ -484,7 +495,7 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
                 d.V, reinterpret_cast<unsigned short*>(sc.dl), sc.rowscale);
             *launches += 1;
         }
-        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.count = sc.count; p.rowscale = sc.rowscale;
+        p.slot = sc.slot; p.tile_of_slot = sc.tile_of_slot; p.slot_meta = sc.slot_meta; p.count = sc.count; p.rowscale = sc.rowscale;
         p.NP = bg.NP; p.NCZ = bg.NCZ; p.priv = bg.priv; p.sh = bg.sh; p.odd_base = bg.odd_base; p.dz_stages = bg.dz_stages;
         p.d_enc = d_enc; p.ppred = sc.ppl;
         p.nVT = bg.nVT; p.nItems = bg.nItems; p.nHB = bg.nHB; p.S = bg.S_max; p.Hrows = d.H;
@@ -497,7 +508,8 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             const int nruns = nb * g.nTb;
             ScopedTimer tmr("bwd_dz_kernel", s);
             p.prof = prof_dz;
-            bwd_dz_kernel<<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
+            if (p.prof) bwd_dz_kernel<true><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
+            else bwd_dz_kernel<false><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
         }
         {
             const size_t n4 = (size_t)nb * d.maxU * d.H / 4;
@@ -508,7 +520,8 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
         {
             ScopedTimer tmr("bwd_dw_kernel", s);
             p.prof = prof_dw;
-            bwd_dw_kernel<<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
+            if (p.prof) bwd_dw_kernel<true><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
+            else bwd_dw_kernel<false><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
         }
         *launches += 3;
         if (cudaGetLastError() != cudaSuccess) return RNNT_STATUS_EXECUTION_FAILED;
