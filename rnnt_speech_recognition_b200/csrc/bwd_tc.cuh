@@ -29,7 +29,7 @@ namespace rb {
 
 constexpr int BW_TT = 16, BW_UU = 8;
 constexpr int DZ_THREADS = 352;      // warp 0 operand TMA | 1 MMA | 2-9 epilogue | 10 enc/pred TMA for the epilogue
-constexpr int DZ_MAX_STAGES = 3;
+constexpr int DZ_MAX_STAGES = 6;
 constexpr int DW_THREADS = 576;      // warp 0 TMA | 1 MMA | 2-17 z producers, then epilogue (16 warps: the tanh chain is latency-bound at 2 warps per scheduler)
 constexpr int DW_STAGES = 3;
 constexpr int DW_NV = 256;           // vocabulary columns per dW output tile
@@ -47,7 +47,7 @@ struct BwdParams {
     const float* rowscale;      // per row of the kept arrays: rs_row (0 for rows outside the lattice)   [row_scale_kernel]
     // ---- dZ kernel
     int NP, NCZ, priv, sh, odd_base;   // passes over H, columns per pass, private / shared accumulator columns
-    int dz_stages;                     // operand ring depth (3, or 2 when the pass is too wide for three stages)
+    int dz_stages;                     // operand ring depth
     float* d_enc;               // (B, maxT, H), rows of this launch's utterances are fully written
     float* ppred;               // (nTb, nb, maxU, H) partial planes of d_pred
     // ---- dW kernel
@@ -68,7 +68,16 @@ struct BwdParams {
 // valid tiles along u; inside a tile NP passes over H.  Accumulators: an even unit uses TMEM columns [0, NCZ), an odd
 // unit [priv .. NCZ) (the SHARED zone, drained first by the epilogue) + [odd_base, 512): two units are in flight
 // (MMA of unit q+1 over the epilogue of unit q) although 2*NCZ may exceed the 512 columns.
-template <bool PROF>
+//
+// PAIR = true: a thread-block cluster of 2 runs the kernel as ONE M = 256 machine (tcgen05 cta_group::2).  The kernel is bound by
+// the L2 -> SM operand stream (1.79 MB per tile at H = 640, V = 1024: 29 GB per launch at C3, at the ~6.3 KB / clk the L2 can
+// deliver), two thirds of it the W rows every tile re-reads.  The pair walks a run's u-blocks two at a time (CTA r owns
+// u-block 2j + r) and shares ONE copy of every W stage: each CTA loads its own E' rows and HALF of the W rows, all bytes are
+// counted on the leader's stage_full, the leader's MMA warp issues for both, the commits are multicast to both CTAs, and the
+// epilogues of both CTAs release the accumulators on the leader's barriers.  With an odd number of u-blocks the last step's
+// second CTA is padding: it loads the leader's rows again, takes part in every handshake and stores nothing.  The two CTAs'
+// partial d_enc rows meet in global memory as two atomic adds onto the zeroed array (two addends: order-independent).
+template <bool PROF, bool PAIR>
 __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_constant__ CUtensorMap tmap_e,
                                                                const __grid_constant__ CUtensorMap tmap_wp,
                                                                const __grid_constant__ CUtensorMap tmap_ws,
@@ -78,7 +87,15 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int NCZ = p.NCZ, NP = p.NP, priv = p.priv, sh = p.sh, KBV = p.V >> 6, DZ_STAGES = p.dz_stages, nch = NCZ >> 5;
-    const uint32_t stage_bytes = 16384u + (uint32_t)NCZ * 128u;            // A [128 rows x 64 v] | B [NCZ h x 64 v]
+    const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int hP = PAIR ? priv >> 1 : priv, hS = PAIR ? sh >> 1 : sh;       // W rows of the private / shared zone THIS CTA loads
+    const uint32_t stage_bytes = 16384u + (uint32_t)(hP + hS) * 128u;       // A [128 rows x 64 v] | B [hP + hS rows of W x 64 v]
+    const int cta0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, cstep = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    auto arrive_leader = [&](uint64_t* bar) {      // the leader's copy of a barrier collects both CTAs
+        if (!PAIR || leader) ptx::mbar_arrive(bar);
+        else ptx::mbar_arrive_cluster(ptx::mapa_u32(bar, 0));
+    };
     // the unit's enc / pred rows for the epilogue's (1 - tanh^2): per 32-column chunk a pred box [32 fp32 x 8 rows] (1 KB,
     // SWIZZLE_128B) and an enc box [32 fp32 x 16 rows] (2 KB), loaded by warp 10 while the unit's MMAs run (measured before:
     // reading them with LDG put 54 % of the epilogue's stall samples on the L2 latency)
@@ -100,15 +117,19 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     if (threadIdx.x == 0) {
         for (int i = 0; i < DZ_MAX_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&stage_empty[i], 1); }
         ptx::mbar_init(epi_full, 1); ptx::mbar_init(epi_empty, 8);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], 8); }
-        ptx::mbar_init(shared_free, 8);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], PAIR ? 16 : 8); }
+        ptx::mbar_init(shared_free, PAIR ? 16 : 8);
         ptx::fence_barrier_init();
     }
-    if (warp == 1) { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
+    if (warp == 1) {
+        if (PAIR) { ptx::tmem_alloc2(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
+    }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_e); ptx::prefetch_tmap(&tmap_wp); ptx::prefetch_tmap(&tmap_ws); }
     if (warp == 10 && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
     ptx::tc_fence_before();
     __syncthreads();
+    if (PAIR) ptx::cluster_sync();       // the peer's barriers exist before anyone arrives on them remotely
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const int nruns = p.nb * p.nTb;
@@ -120,23 +141,33 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         // ===================== TMA: A = kept numerators [128 rows x 64 v], B = W rows [NCZ h x 64 v] =====================
         if (lane == 0) {
             int stage = 0; uint32_t phase = 0;
-            for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+            for (int run = cta0; run < nruns; run += cstep) {
                 const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
                 const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
                 if (tb * BW_TT >= Tn) continue;
-                const int nub = (Un + BW_UU - 1) / BW_UU;
-                for (int ub = 0; ub < nub; ++ub) {
+                const int nub = (Un + BW_UU - 1) / BW_UU, nq = PAIR ? (nub + 1) >> 1 : nub;
+                for (int j = 0; j < nq; ++j) {
+                    const int ub = PAIR ? min(2 * j + (int)rank, nub - 1) : j;     // a padding CTA loads the leader's rows again
                     const int tile = (bl * p.nTb + tb) * p.nUb + ub;
                     const int sl = p.slot ? p.slot[tile] : tile;
                     for (int pass = 0; pass < NP; ++pass) {
                         const int n0 = pass * NCZ;
                         for (int kb = 0; kb < KBV; ++kb) {
                             { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
-                            ptx::mbar_arrive_expect_tx(&stage_full[stage], stage_bytes);
                             uint8_t* st = smem + (size_t)stage * stage_bytes;
-                            ptx::tma_load_2d(st, &tmap_e, &stage_full[stage], kb * 64, sl * 128);
-                            ptx::tma_load_2d(st + 16384, &tmap_wp, &stage_full[stage], kb * 64, n0);
-                            if (sh) ptx::tma_load_2d(st + 16384 + (size_t)priv * 128, &tmap_ws, &stage_full[stage], kb * 64, n0 + priv);
+                            if (PAIR) {
+                                // both CTAs' bytes complete on the LEADER's barrier; only the leader posts the expected count
+                                if (leader) ptx::mbar_arrive_expect_tx(&stage_full[stage], 2u * stage_bytes);
+                                const uint32_t bar = ptx::mapa_u32(&stage_full[stage], 0);
+                                ptx::tma_load_2d_2sm(st, &tmap_e, bar, kb * 64, sl * 128);
+                                ptx::tma_load_2d_2sm(st + 16384, &tmap_wp, bar, kb * 64, n0 + (int)rank * hP);
+                                if (sh) ptx::tma_load_2d_2sm(st + 16384 + (size_t)hP * 128, &tmap_ws, bar, kb * 64, n0 + priv + (int)rank * hS);
+                            } else {
+                                ptx::mbar_arrive_expect_tx(&stage_full[stage], stage_bytes);
+                                ptx::tma_load_2d(st, &tmap_e, &stage_full[stage], kb * 64, sl * 128);
+                                ptx::tma_load_2d(st + 16384, &tmap_wp, &stage_full[stage], kb * 64, n0);
+                                if (sh) ptx::tma_load_2d(st + 16384 + (size_t)priv * 128, &tmap_ws, &stage_full[stage], kb * 64, n0 + priv);
+                            }
                             if (++stage == DZ_STAGES) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -145,14 +176,15 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         }
     } else if (warp == 1) {
         // ===================== MMA: D[128 x NCZ] += A[128 x 64] . B[NCZ x 64]^T, both operands K-major in smem =====================
-        const uint32_t idescP = ptx::umma_idesc_bf16(128, priv), idescS = ptx::umma_idesc_bf16(128, sh ? sh : 16);
+        const uint32_t idescP = ptx::umma_idesc_bf16(PAIR ? 256 : 128, priv), idescS = ptx::umma_idesc_bf16(PAIR ? 256 : 128, sh ? sh : 16);
         int stage = 0; uint32_t phase = 0, q = 0;
-        for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        if (!PAIR || leader)
+        for (int run = cta0; run < nruns; run += cstep) {
             const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
             const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
             if (tb * BW_TT >= Tn) continue;
-            const int nub = (Un + BW_UU - 1) / BW_UU;
-            for (int ub = 0; ub < nub; ++ub)
+            const int nub = (Un + BW_UU - 1) / BW_UU, nq = PAIR ? (nub + 1) >> 1 : nub;
+            for (int j = 0; j < nq; ++j)
                 for (int pass = 0; pass < NP; ++pass, ++q) {
                     const uint32_t par = q & 1;
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&priv_free[par], ((q >> 1) & 1) ^ 1); RB_PROF_END(pf, pc[0]); }
@@ -162,11 +194,13 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                         { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_full[stage], phase); RB_PROF_END(pf, pc[1]); }
                         const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * stage_bytes);
                         const uint64_t ad = ptx::umma_desc_k_sw128(sa), bp = ptx::umma_desc_k_sw128(sa + 16384u),
-                                       bs = ptx::umma_desc_k_sw128(sa + 16384u + (uint32_t)priv * 128u);
+                                       bs = ptx::umma_desc_k_sw128(sa + 16384u + (uint32_t)hP * 128u);
                         if (ptx::elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < 4; ++k)
-                                ptx::umma_bf16(dP, ad + (uint64_t)(k * 2), bp + (uint64_t)(k * 2), idescP, (uint32_t)((kb | k) != 0));
+                            for (int k = 0; k < 4; ++k) {
+                                if (PAIR) ptx::umma_ss2(dP, ad + (uint64_t)(k * 2), bp + (uint64_t)(k * 2), idescP, (uint32_t)((kb | k) != 0));
+                                else ptx::umma_bf16(dP, ad + (uint64_t)(k * 2), bp + (uint64_t)(k * 2), idescP, (uint32_t)((kb | k) != 0));
+                            }
                         }
                         __syncwarp();
                         if (sh) {
@@ -178,14 +212,21 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                             }
                             if (ptx::elect_one()) {
 #pragma unroll
-                                for (int k = 0; k < 4; ++k)
-                                    ptx::umma_bf16(dS, ad + (uint64_t)(k * 2), bs + (uint64_t)(k * 2), idescS, (uint32_t)((kb | k) != 0));
+                                for (int k = 0; k < 4; ++k) {
+                                    if (PAIR) ptx::umma_ss2(dS, ad + (uint64_t)(k * 2), bs + (uint64_t)(k * 2), idescS, (uint32_t)((kb | k) != 0));
+                                    else ptx::umma_bf16(dS, ad + (uint64_t)(k * 2), bs + (uint64_t)(k * 2), idescS, (uint32_t)((kb | k) != 0));
+                                }
                             }
                             __syncwarp();
                         }
                         if (ptx::elect_one()) {
-                            ptx::umma_commit(&stage_empty[stage]);
-                            if (kb == KBV - 1) ptx::umma_commit(&acc_full[par]);
+                            if (PAIR) {
+                                ptx::umma_commit2_mc(&stage_empty[stage], 3);
+                                if (kb == KBV - 1) ptx::umma_commit2_mc(&acc_full[par], 3);
+                            } else {
+                                ptx::umma_commit(&stage_empty[stage]);
+                                if (kb == KBV - 1) ptx::umma_commit(&acc_full[par]);
+                            }
                         }
                         __syncwarp();
                         if (++stage == DZ_STAGES) { stage = 0; phase ^= 1; }
@@ -196,12 +237,12 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         // ===================== enc / pred TMA for the epilogue: one unit ahead of it =====================
         if (lane == 0) {
             uint32_t uq = 0;
-            for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+            for (int run = cta0; run < nruns; run += cstep) {
                 const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
                 const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
                 if (tb * BW_TT >= Tn) continue;
                 const int nub = (Un + BW_UU - 1) / BW_UU;
-                for (int ub = 0; ub < nub; ++ub)
+                for (int ub = PAIR ? (int)rank : 0; ub < nub; ub += PAIR ? 2 : 1)     // live tiles of this CTA only
                     for (int pass = 0; pass < NP; ++pass, ++uq) {
                         ptx::mbar_wait(epi_empty, (uq & 1) ^ 1);
                         ptx::mbar_arrive_expect_tx(epi_full, (uint32_t)nch * 3072u);
@@ -223,8 +264,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         const int off4 = (ul & 1) * 16 + ((ul >> 1) & 1) * 8 + ((ul >> 2) & 1) * 4;   // columns this lane keeps after the u butterfly
         const int cbase = ((lane >> 3) & 1) * 16 + ((lane >> 4) & 1) * 8;              // ... after the t butterfly
         const uint32_t enc_a = ptx::smem_u32(encb) + (uint32_t)(r >> 3) * 128u, pred_a = ptx::smem_u32(predb) + (uint32_t)ul * 128u;
-        uint32_t q = 0, nchunk = 0;
-        for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        uint32_t q = 0, nchunk = 0, eq = 0;      // q counts the pair's units (accumulator parity), eq this CTA's live units (enc / pred boxes)
+        for (int run = cta0; run < nruns; run += cstep) {
             const int bl = run / p.nTb, tb = run - bl * p.nTb, b = p.b0 + bl;
             const int Tn = p.xlen[b], Un = p.ylen[b] + 1;
             if (tb * BW_TT >= Tn) continue;
@@ -237,7 +278,23 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                 for (int j = 0; j < 6; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) accE[a][j][i] = 0.f;
-            for (int ub = 0; ub < nub; ++ub) {
+            const int nq = PAIR ? (nub + 1) >> 1 : nub;
+            for (int jq = 0; jq < nq; ++jq) {
+                const int ub = PAIR ? 2 * jq + (int)rank : jq;
+                if (PAIR && ub >= nub) {
+                    // padding half of the run's last step: release the accumulators the leader's MMAs wrote here, nothing else
+                    for (int pass = 0; pass < NP; ++pass, ++q) {
+                        ptx::mbar_wait(&acc_full[q & 1], (q >> 1) & 1);
+                        ptx::tc_fence_after();
+                        ptx::tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (nsh_h > 0) arrive_leader(shared_free);
+                            arrive_leader(&priv_free[q & 1]);
+                        }
+                    }
+                    continue;
+                }
                 const int tile = (bl * p.nTb + tb) * p.nUb + ub;
                 const float rs = __ldg(p.rowscale + (size_t)(p.slot ? p.slot[tile] : tile) * 128 + r);   // 0 outside the lattice
 #pragma unroll
@@ -246,7 +303,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     const uint32_t par = q & 1;
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(&acc_full[par], (q >> 1) & 1); RB_PROF_END(pf, pc[0]); }
                     ptx::tc_fence_after();
-                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(epi_full, q & 1); RB_PROF_END(pf, pc[2]); }
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(epi_full, eq & 1); RB_PROF_END(pf, pc[2]); }
                     const int n0 = pass * NCZ;
 #pragma unroll
                     for (int j = 0; j < 6; ++j) {
@@ -260,8 +317,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                             ptx::tc_fence_before();
                             __syncwarp();
                             if (lane == 0) {
-                                if (j == nsh_h - 1) ptx::mbar_arrive(shared_free);
-                                if (j == nj - 1) ptx::mbar_arrive(&priv_free[par]);
+                                if (j == nsh_h - 1) arrive_leader(shared_free);
+                                if (j == nj - 1) arrive_leader(&priv_free[par]);
                             }
                         }
                         const int h0 = n0 + 32 * c;
@@ -333,7 +390,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     }
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(epi_empty);      // this warp has read the unit's enc / pred rows
-                    ++q;
+                    ++q; ++eq;
                 }
             }
             // ---- the run is complete: this lane owns (t, 4 columns per chunk) of d_enc
@@ -346,8 +403,9 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     for (int j = 0; j < 6; ++j) {
                         if (j >= nj) continue;
                         const int c = j < nsh_h ? npr + 2 * j + hh : 2 * (j - nsh_h) + hh;
-                        *reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4) =
-                            make_float4(accE[pass][j][0], accE[pass][j][1], accE[pass][j][2], accE[pass][j][3]);
+                        const float4 v4 = make_float4(accE[pass][j][0], accE[pass][j][1], accE[pass][j][2], accE[pass][j][3]);
+                        if (PAIR) atomicAdd(reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4), v4);    // the two CTAs' halves of the run
+                        else *reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4) = v4;
                     }
                 }
             }
@@ -359,7 +417,11 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     }
     ptx::tc_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (PAIR) ptx::cluster_sync();       // no CTA leaves while its peer may still arrive on its barriers
+    if (warp == 1) {
+        if (PAIR) ptx::tmem_dealloc2(tmem_base, TC_TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    }
 }
 
 // d_pred[b,u,:] = sum over the t-blocks that intersect the utterance of its partial planes (0 for u >= U_b)

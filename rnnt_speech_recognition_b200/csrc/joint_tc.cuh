@@ -66,7 +66,13 @@ struct BwdGeom {
     int nVT, nHB, nItems, S_max, dw_grid;     // S_max = the split count S
     bool ok;
 };
-inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
+// dZ kernel variant: 2 (default) = CTA pairs (cta_group::2, one copy of each W stage per two tiles), 1 = one CTA per tile
+inline int tc_dz_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_DZ"); v = e ? atoi(e) : 2; if (v != 1 && v != 2) v = 2; }
+    return v;
+}
+inline BwdGeom bwd_geometry(int H, int V, int sms = 148, bool dz_pair = true) {
     BwdGeom g{};
     g.ok = false;
     if (H % 64 || V % 64 || H > 768 || H < 64) return g;
@@ -75,8 +81,10 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148) {
     g.sh = 2 * g.NCZ > 512 ? 2 * g.NCZ - 512 : 0;
     g.priv = g.NCZ - g.sh;
     g.odd_base = 512 - g.priv;
-    for (g.dz_stages = 3; g.dz_stages >= 2; --g.dz_stages) {
-        g.dz_smem = 1024 + (size_t)g.dz_stages * (16384 + (size_t)g.NCZ * 128) + (size_t)(g.NCZ / 32) * 3072 + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+    // operand stage: the tile's E' block (16 KB) + the W rows this CTA loads (all NCZ of the pass, or half of them in a pair)
+    const size_t dz_stage = 16384 + (size_t)(dz_pair ? g.NCZ / 2 : g.NCZ) * 128;
+    for (g.dz_stages = dz_pair ? 6 : 3; g.dz_stages >= 2; --g.dz_stages) {
+        g.dz_smem = 1024 + (size_t)g.dz_stages * dz_stage + (size_t)(g.NCZ / 32) * 3072 + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
         if (g.dz_smem <= 232448) break;
     }
     g.dw_smem = 1024 + (size_t)3 * 65536 + 8 * 256 + 512;
@@ -287,7 +295,7 @@ inline size_t tc_chunk_budget() {
 inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     TcScratch s{};
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
-    const BwdGeom bg = bwd_geometry(d.H, d.V);
+    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2);
     const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
     const size_t per_row = (size_t)d.V * 2 + 8;
     size_t bc = tc_chunk_budget() / (rows_utt * per_row);
@@ -377,7 +385,7 @@ inline long long* tc_prof_buffer(int which) {
 }
 
 inline bool tc_supported(const rnntb200JointDesc& d) {
-    return tc_geometry(d.maxT, d.maxU, d.H, d.V).ok && tc3_geometry(d.H, d.V).ok && bwd_geometry(d.H, d.V).ok;
+    return tc_geometry(d.maxT, d.maxU, d.H, d.V).ok && tc3_geometry(d.H, d.V).ok && bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2).ok;
 }
 inline size_t tc_scratch_bytes(const rnntb200JointDesc& d) {
     if (!tc_supported(d)) return 0;
@@ -459,11 +467,13 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
                                 float* db, cudaStream_t s, unsigned* launches) {
     if (!tc_supported(d)) return tc_unsupported(d);
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
-    const BwdGeom bg = bwd_geometry(d.H, d.V);
+    const bool dz_pair = tc_dz_variant() == 2;
+    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, dz_pair);
     TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
     const bool kept = tc_keep(d, sc);
-    if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<false>)) ||
-        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<true>)))
+    if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false, false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true, false>)) ||
+        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false, true>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true, true>)) ||
+        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<true>)))
         return RNNT_STATUS_EXECUTION_FAILED;
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
@@ -472,7 +482,8 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
     if (!make_tmap_f32(&tm_p32, pred, (uint64_t)d.B * d.maxU, d.H, BW_UU, 32, true) ||
         !make_tmap_f32(&tm_e32, enc, (uint64_t)d.B * d.maxT, d.H, BW_TT, 32, false) ||
         !make_tmap_bf16(&tm_e128, sc.dl, sc.rows_chunk, d.V, 128) || !make_tmap_bf16(&tm_e64, sc.dl, sc.rows_chunk, d.V, 64) ||
-        !make_tmap_bf16(&tm_wp, sc.Wb, d.H, d.V, bg.priv) || !make_tmap_bf16(&tm_ws, sc.Wb, d.H, d.V, bg.sh ? bg.sh : 8)) {
+        !make_tmap_bf16(&tm_wp, sc.Wb, d.H, d.V, dz_pair ? bg.priv / 2 : bg.priv) ||
+        !make_tmap_bf16(&tm_ws, sc.Wb, d.H, d.V, bg.sh ? (dz_pair ? bg.sh / 2 : bg.sh) : 8)) {
         fprintf(stderr, "rnnt_b200: cuTensorMapEncodeTiled failed\n");
         return RNNT_STATUS_EXECUTION_FAILED;
     }
@@ -508,8 +519,19 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
             const int nruns = nb * g.nTb;
             ScopedTimer tmr("bwd_dz_kernel", s);
             p.prof = prof_dz;
-            if (p.prof) bwd_dz_kernel<true><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
-            else bwd_dz_kernel<false><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
+            if (dz_pair) {
+                const int npairs = nruns < sms / 2 ? nruns : sms / 2;
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = dim3(2 * npairs); cfg.blockDim = dim3(DZ_THREADS); cfg.dynamicSmemBytes = bg.dz_smem; cfg.stream = s;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                if (cudaLaunchKernelEx(&cfg, p.prof ? bwd_dz_kernel<true, true> : bwd_dz_kernel<false, true>, tm_e128, tm_wp, tm_ws, tm_p32,
+                                       tm_e32, p) != cudaSuccess)
+                    return RNNT_STATUS_EXECUTION_FAILED;
+            } else if (p.prof) bwd_dz_kernel<true, false><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
+            else bwd_dz_kernel<false, false><<<nruns < sms ? nruns : sms, DZ_THREADS, bg.dz_smem, s>>>(tm_e128, tm_wp, tm_ws, tm_p32, tm_e32, p);
         }
         {
             const size_t n4 = (size_t)nb * d.maxU * d.H / 4;

@@ -191,6 +191,15 @@ __device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint6
         ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// D[tmem of both CTAs] (+)= A[smem, 128 rows in each CTA] . B[smem, N/2 rows in each CTA]^T, M = 256 (descriptors are CTA-local
+// offsets, applied in both CTAs)
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // all previously issued cta_group::2 MMAs of this thread complete -> one arrive on the barrier at this offset in every CTA of the mask
 __device__ __forceinline__ void umma_commit2_mc(uint64_t* bar, uint16_t cta_mask) {
     asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
@@ -202,6 +211,13 @@ __device__ __forceinline__ void tma_load_3d_2sm(void* smem_dst, const void* tmap
     asm volatile(
         "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
         ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const void* tmap, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
         : "memory");
 }
 
