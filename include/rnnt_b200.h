@@ -196,6 +196,19 @@ rnntStatus_t rnntb200_joint_step(const float* f, long long ldf, const float* g, 
                                  const float* b1, const float* K2, const float* b2, int B, int P, int H, int V,
                                  float* logits, int* best, float* best_logp, CUstream stream);
 
+/** Dense-1 of the joint (model.py:162-163, Keras kernel (P,H) + bias (H)) applied BEFORE the broadcast add -- it is linear in
+ *  front of its tanh, so W1^T (f_t + g_u) + b1 = (W1^T f_t + b1) + W1^T g_u: the hot path's inputs
+ *  enc_acts / pred_acts are these two projections.
+ *    forward:   out[r,:] = X[r,:] . K1 (+ b1)                       X (rows,P) -> out (rows,H), b1 may be NULL (the pred side)
+ *    backward:  dX = dA . K1^T;  dK1 += X^T . dA;  db1 += sum_r dA[r,:]      (dX, dK1, db1 may each be NULL; dK1 / db1 are
+ *               ACCUMULATED into, so the encoder-side and the prediction-side call add into one zeroed buffer)
+ *  fp32 FMA kernels of this library (no GEMM library).  dK1 is a split-K product combined with float atomics: its last bits
+ *  depend on the order the partial sums arrive in (as the exact fp32 path's dW). */
+rnntStatus_t rnntb200_dense1_forward(const float* X, long long rows, int P, const float* K1, const float* b1, int H,
+                                     float* out, CUstream stream);
+rnntStatus_t rnntb200_dense1_backward(const float* X, const float* dA, const float* K1, long long rows, int P, int H,
+                                      float* dX, float* dK1, float* db1, CUstream stream);
+
 /** Number of kernels launched by this library in this process since load (bench.py's gpu_launches).  Every kernel
  *  on the path is the library's own: it links no GEMM library. */
 unsigned long long rnntb200_launch_count();

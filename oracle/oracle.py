@@ -110,6 +110,19 @@ def joint_forward(enc, pred, W, bias):
     return out
 
 
+def joint_step(f, g, K1, b1, K2, b2):
+    """Greedy-decode joint of ONE lattice cell per batch row in float64 numpy (utils/decoding.py:6-18 followed by the
+    log_softmax + argmax of utils/decoding.py:69-78): returns (logits (B,V), argmax (B,), log-softmax value at the argmax (B,)).
+    ``K1 is None``: f, g are already-projected activations."""
+    x = np.asarray(f, np.float64) + np.asarray(g, np.float64)
+    z = np.tanh(x @ np.asarray(K1, np.float64) + (0.0 if b1 is None else np.asarray(b1, np.float64))) if K1 is not None else np.tanh(x)
+    y = z @ np.asarray(K2, np.float64) + (0.0 if b2 is None else np.asarray(b2, np.float64))
+    m = y.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(y - m).sum(axis=1))
+    best = y.argmax(axis=1)
+    return y, best.astype(np.int32), y[np.arange(len(y)), best] - lse
+
+
 def joint_loss_grad(enc, pred, W, bias, labels, input_lengths, label_lengths, blank=0, grad_scale=None,
                     want_grad=True):
     """Whole hot path: returns dict(costs, d_enc, d_pred, dW, db)."""

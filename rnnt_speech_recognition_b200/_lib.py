@@ -29,6 +29,7 @@ class JointDesc(C.Structure):
 EXPORTS = ("get_warprnnt_version", "rnntGetStatusString", "get_workspace_size", "compute_rnnt_loss",
            "compute_rnnt_loss_fp64", "rnntb200_loss_device", "rnntb200_joint_workspace_size",
            "rnntb200_joint_loss_forward", "rnntb200_joint_loss_backward", "rnntb200_joint_logits", "rnntb200_joint_step",
+           "rnntb200_dense1_forward", "rnntb200_dense1_backward",
            "rnntb200_launch_count", "rnntb200_build_info", "rnntb200_set_timing", "rnntb200_get_timing")
 
 _lib = None
@@ -66,6 +67,8 @@ def load(build_if_missing=True):
     L.rnntb200_joint_loss_backward.argtypes = [C.POINTER(JointDesc)] + [vp] * 13
     L.rnntb200_joint_logits.argtypes = [C.POINTER(JointDesc)] + [vp] * 6
     L.rnntb200_joint_step.argtypes = [vp, C.c_longlong, vp, C.c_longlong, vp, vp, vp, vp, ci, ci, ci, ci, vp, vp, vp, vp]
+    L.rnntb200_dense1_forward.argtypes = [vp, C.c_longlong, ci, vp, vp, ci, vp, vp]
+    L.rnntb200_dense1_backward.argtypes = [vp, vp, vp, C.c_longlong, ci, ci, vp, vp, vp, vp]
     L.rnntb200_launch_count.restype = C.c_ulonglong
     L.rnntb200_build_info.restype = C.c_char_p
     L.rnntb200_set_timing.argtypes = [ci]

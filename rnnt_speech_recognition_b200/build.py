@@ -9,7 +9,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "rnnt_b200.cu")
 OUT = os.environ.get("RNNTB200_BUILD_OUT") or os.path.join(HERE, "librnnt_b200.so")
-DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in ("kernels_simt.cuh", "joint_tc.cuh", "joint_tc3.cuh", "bwd_tc.cuh", "ptx.cuh", "timing.cuh")] + [
+DEPS = [SRC] + [os.path.join(HERE, "csrc", f) for f in sorted(os.listdir(os.path.join(HERE, "csrc"))) if f.endswith(".cuh")] + [
     os.path.join(os.path.dirname(HERE), "include", "rnnt_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
               "-Xcompiler", "-fPIC", "-diag-suppress", "177"]

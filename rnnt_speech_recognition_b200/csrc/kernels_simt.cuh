@@ -422,6 +422,23 @@ __global__ void __launch_bounds__(256) zgen_kernel(const float* __restrict__ enc
     }
 }
 
+// out[n] += sum_r A[r, n] for a row-major (rows, N) matrix: one block per 32 columns, 8 row lanes, fixed summation order
+__global__ void __launch_bounds__(256) colsum_add_kernel(const float* __restrict__ A, long long rows, int N, float* __restrict__ out) {
+    __shared__ float part[8][33];
+    const int c = threadIdx.x & 31, rl = threadIdx.x >> 5, n = blockIdx.x * 32 + c;
+    float acc = 0.f;
+    if (n < N)
+        for (long long r = rl; r < rows; r += 8) acc += A[r * N + n];
+    part[rl][c] = acc;
+    __syncthreads();
+    if (rl == 0 && n < N) {
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += part[k][c];
+        out[n] += s;
+    }
+}
+
 // C[m,n] = (accumulate ? C : 0) + sum_k A(m,k) B(k,n) (+ bias[n]); generic strides so that the three
 // products of the exact path (Z.W, dL.W^T, Z^T.dL) share one kernel.  64x64x16 tiles, 256 threads,
 // 4x4 register micro-tiles; the smem tile loads pick the thread mapping by which stride is unit.

