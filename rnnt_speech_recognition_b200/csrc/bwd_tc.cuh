@@ -684,4 +684,245 @@ __global__ void __launch_bounds__(DW_THREADS, 1) bwd_dw_kernel(const __grid_cons
     if (warp == 1) ptx::tmem_dealloc(tmem_base, TC_TMEM_COLS);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// dW kernel, CTA-pair form (default)
+// ---------------------------------------------------------------------------------------------------------------
+// The one-CTA kernel above regenerates every z tile once per 256-column v-tile (4 x at V = 1024) and its 16 producer warps,
+// not the tensor pipe, set its pace (measured: 1420 cycles of tanh per K step against 1048 cycles of MMA).  A wider output tile
+// per z tile needs more accumulator columns than one CTA has for two row blocks, so here a CLUSTER OF 2 owns the two block
+// slots of an h-item: CTA r regenerates block 2*item + r ONCE per K step and multiplies it against 512 columns of E'
+// (tcgen05 cta_group::2, M = 256: rows 0-127 accumulate in CTA 0's tensor memory, rows 128-255 in CTA 1's, all 512 columns
+// each).  Per K step and CTA: 8 k tanh instead of 16 k, the same 32 KB of E' (each CTA loads half of the columns of both
+// N = 256 instructions), the same 1024 cycles of tensor pipe -- which now is the bound.  Barriers as in the dZ pair kernel.
+constexpr int DW2_STAGES = 4;
+constexpr int DW2_NV = 512;
+constexpr uint32_t DW2_STAGE = 49152u;      // A [128 x 64 k] K-major (16 KB) | B: 2 instructions x 2 boxes [64 k x 64 v] MN-major (32 KB)
+
+template <bool PROF>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(DW_THREADS, 1) bwd_dw2_kernel(const __grid_constant__ CUtensorMap tmap_e, const BwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* rsring = smem + DW2_STAGES * DW2_STAGE;            // [DW_NRS][64] floats
+    uint64_t* bars = reinterpret_cast<uint64_t*>(rsring + DW_NRS * 256);
+    uint64_t* b_full = bars;                       // [stages] both CTAs' TMA -> leader's MMA
+    uint64_t* a_ready = b_full + DW2_STAGES;       // both CTAs' producers -> leader's MMA
+    uint64_t* stage_empty = a_ready + DW2_STAGES;  // MMA (multicast commit) -> TMA, producers of both CTAs
+    uint64_t* rs_full = stage_empty + DW2_STAGES;  // [DW_NRS] TMA -> producers (local)
+    uint64_t* rs_empty = rs_full + DW_NRS;         // [DW_NRS] producers -> TMA (local)
+    uint64_t* acc_full = rs_empty + DW_NRS;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();
+    const bool leader = rank == 0;
+    DwWork wk;
+    {
+        const int pair = blockIdx.x >> 1, per_vt = p.nItems * p.S;
+        wk.vt = pair / per_vt;
+        const int rem = pair - wk.vt * per_vt;
+        wk.item = rem / p.S;
+        wk.split = rem - wk.item * p.S;
+    }
+    const int v0 = wk.vt * DW2_NV, Nv = min(DW2_NV, p.V - v0);
+    // the two N <= 256 instructions of a K step; N is rounded up to whole 64-column boxes per CTA (columns past V are
+    // zero-filled by the TMA and never stored)
+    const int N0 = min(256, (Nv + 127) & ~127), N1 = Nv > 256 ? (Nv - 256 + 127) & ~127 : 0;
+    const int nb0 = N0 >> 7, nb1 = N1 >> 7;        // boxes per CTA and instruction
+    const int kind = dw_kind(p, wk.item, (int)rank), kind_peer = dw_kind(p, wk.item, (int)rank ^ 1);
+    auto warps_of = [](int k) { return k == 0 ? 16 : (k == 1 ? 1 : 0); };      // producer warps that arrive per K step
+    const int narr = warps_of(kind), narr_pair = narr + warps_of(kind_peer);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < DW2_STAGES; ++i) {
+            ptx::mbar_init(&b_full[i], 1); ptx::mbar_init(&a_ready[i], narr_pair ? narr_pair : 1); ptx::mbar_init(&stage_empty[i], 1);
+        }
+        for (int i = 0; i < DW_NRS; ++i) { ptx::mbar_init(&rs_full[i], 1); ptx::mbar_init(&rs_empty[i], narr ? narr : 1); }
+        ptx::mbar_init(acc_full, 1);
+        ptx::fence_barrier_init();
+    }
+    // A tiles of a SCALE block (rows 1..127 stay zero, row 0 is rewritten every K step) and of an empty slot (all zero)
+    if (kind != 0)
+        for (int st = 0; st < DW2_STAGES; ++st)
+            for (int i = threadIdx.x; i < 16384 / 16; i += DW_THREADS)
+                reinterpret_cast<uint4*>(smem + (size_t)st * DW2_STAGE)[i] = make_uint4(0u, 0u, 0u, 0u);
+    ptx::fence_proxy_async_smem();
+    if (warp == 1) { ptx::tmem_alloc2(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish2(); }
+    if (warp == 0 && lane == 0) ptx::prefetch_tmap(&tmap_e);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const long long cnt = *p.count;
+    const int s_beg = (int)(cnt * wk.split / p.S), s_end = (int)(cnt * (wk.split + 1) / p.S);
+    const int nsteps = 2 * (s_end - s_beg);
+    const bool pf = PROF && p.prof != nullptr && (lane == 0) && (warp == 0 || warp == 1 || warp == 2);
+    long long pc[4] = {0, 0, 0, 0};
+    const long long t_start = pf ? clock64() : 0;
+    auto arrive_leader = [&](uint64_t* bar) {
+        if (leader) ptx::mbar_arrive(bar);
+        else ptx::mbar_arrive_cluster(ptx::mapa_u32(bar, 0));
+    };
+
+    if (warp == 0) {
+        // ===================== TMA: this CTA's half of the K step's E' columns; the rows' scales run ahead =====================
+        if (lane == 0) {
+            auto load_rs = [&](int k) {
+                const int e = k % DW_NRS;
+                ptx::mbar_wait(&rs_empty[e], ((k / DW_NRS) & 1) ^ 1);
+                ptx::mbar_arrive_expect_tx(&rs_full[e], 256u);
+                ptx::bulk_load_1d(rsring + e * 256, p.rowscale + (size_t)(s_beg + (k >> 1)) * 128 + (k & 1) * 64, 256u, &rs_full[e]);
+            };
+            if (narr)
+                for (int k = 0; k < DW_NRS - DW2_STAGES && k < nsteps; ++k) load_rs(k);
+            const uint32_t tx = (uint32_t)(nb0 + nb1) * 8192u;
+            int stage = 0; uint32_t phase = 0, it = 0;
+            for (int s = s_beg; s < s_end; ++s)
+                for (int half = 0; half < 2; ++half, ++it) {
+                    if (narr && (int)it + DW_NRS - DW2_STAGES < nsteps) load_rs((int)it + DW_NRS - DW2_STAGES);
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
+                    if (leader) ptx::mbar_arrive_expect_tx(&b_full[stage], 2u * tx);
+                    const uint32_t bar = ptx::mapa_u32(&b_full[stage], 0);
+                    uint8_t* bs = smem + (size_t)stage * DW2_STAGE + 16384;
+                    const int row = s * 128 + half * 64;
+                    for (int j = 0; j < nb0; ++j)
+                        ptx::tma_load_2d_2sm(bs + j * 8192, &tmap_e, bar, v0 + (int)rank * (N0 >> 1) + 64 * j, row);
+                    for (int j = 0; j < nb1; ++j)
+                        ptx::tma_load_2d_2sm(bs + 16384 + j * 8192, &tmap_e, bar, v0 + 256 + (int)rank * (N1 >> 1) + 64 * j, row);
+                    if (++stage == DW2_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA (leader): D[256 x Nv] += A[256 x 64 k] . E'[64 k x Nv], two N <= 256 instructions per 16 rows =====================
+        const uint32_t idesc0 = ptx::umma_idesc_bf16(256, N0, 0, 1), idesc1 = ptx::umma_idesc_bf16(256, N1 ? N1 : 128, 0, 1);
+        int stage = 0; uint32_t phase = 0, it = 0;
+        if (leader)
+        for (int s = s_beg; s < s_end; ++s)
+            for (int half = 0; half < 2; ++half, ++it) {
+                { RB_PROF_BEGIN(pf); ptx::mbar_wait(&b_full[stage], phase); RB_PROF_END(pf, pc[0]); }
+                if (narr_pair) { RB_PROF_BEGIN(pf); ptx::mbar_wait(&a_ready[stage], phase); RB_PROF_END(pf, pc[1]); }
+                ptx::tc_fence_after();
+                const uint32_t sa = ptx::smem_u32(smem + (size_t)stage * DW2_STAGE);
+                const uint64_t ad = ptx::umma_desc_k_sw128(sa), bd0 = ptx::umma_desc_mn_sw128(sa + 16384u, 8192u),
+                               bd1 = ptx::umma_desc_mn_sw128(sa + 32768u, 8192u);
+                if (ptx::elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {   // K = 16 lattice rows per MMA: 32 B along A's rows, 16 x 128 B of B
+                        ptx::umma_ss2(tmem_base, ad + (uint64_t)(k * 2), bd0 + (uint64_t)(k * 128), idesc0, (uint32_t)((it | (uint32_t)k) != 0));
+                        if (N1) ptx::umma_ss2(tmem_base + 256u, ad + (uint64_t)(k * 2), bd1 + (uint64_t)(k * 128), idesc1, (uint32_t)((it | (uint32_t)k) != 0));
+                    }
+                    ptx::umma_commit2_mc(&stage_empty[stage], 3);
+                    if (s == s_end - 1 && half == 1) ptx::umma_commit2_mc(acc_full, 3);
+                }
+                __syncwarp();
+                if (++stage == DW2_STAGES) { stage = 0; phase ^= 1; }
+            }
+    } else {
+        // ===================== A producers (warps 2-17): thread = (column h of this CTA's block, 2 of a K step's 8 time rows), or the SCALE row; then the epilogue =====================
+        const int ptid = threadIdx.x - 64, q4 = ptid >> 7, hl = ptid & 127;
+        const int hb = 2 * wk.item + (int)rank, h = hb * 128 + hl;
+        const uint32_t smem_a = ptx::smem_u32(smem);
+        if (kind == 0) {
+            const int hc = min(h, p.H - 1);
+            auto meta_at = [&](int s) { return s < s_end ? __ldg(p.slot_meta + s) : make_int4(0, 0, 1, 1); };
+            float pv[8], ev[4], npv[8], nev[4];     // ev[half * 2 + j] = enc row t0 + half * 8 + q4 * 2 + j
+            auto load = [&](const int4 m, float* pvv, float* evv) {
+                const char* pp = reinterpret_cast<const char*>(p.pred + (size_t)m.y * p.H + hc);
+                const char* pe = reinterpret_cast<const char*>(p.enc + (size_t)m.x * p.H + hc);
+                const uint32_t hb4 = (uint32_t)p.H * 4u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pvv[k] = __ldg(reinterpret_cast<const float*>(pp + (uint32_t)min(k, m.w - 1) * hb4));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    evv[k] = __ldg(reinterpret_cast<const float*>(pe + (uint32_t)min((k >> 1) * 8 + q4 * 2 + (k & 1), m.z - 1) * hb4));
+            };
+            load(meta_at(s_beg), pv, ev);
+            int4 meta_n = meta_at(s_beg + 1);
+            int stage = 0; uint32_t phase = 0, it = 0;
+            for (int s = s_beg; s < s_end; ++s) {
+                const int4 meta_nn = meta_at(s + 2);
+                if (s + 1 < s_end) load(meta_n, npv, nev);
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int e_rs = it % DW_NRS;
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&stage_empty[stage], phase ^ 1); RB_PROF_END(pf, pc[0]); }
+                    { RB_PROF_BEGIN(pf); ptx::mbar_wait(&rs_full[e_rs], (it / DW_NRS) & 1); RB_PROF_END(pf, pc[2]); }
+                    const uint32_t arow = smem_a + (uint32_t)stage * DW2_STAGE + (uint32_t)(hl * 128);
+                    const uint32_t rsa = ptx::smem_u32(rsring) + (uint32_t)e_rs * 256u;
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        const int tl = q4 * 2 + j;
+                        const float e = half ? ev[2 + j] : ev[j];
+                        const float4 r0 = ptx::lds128f(rsa + (uint32_t)(tl * 32)), r1 = ptx::lds128f(rsa + (uint32_t)(tl * 32 + 16));
+                        const float rsv[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+                        float z[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) z[k] = ptx::tanh_approx(e + pv[k]) * rsv[k];
+                        ptx::sts128(arow + (uint32_t)((tl ^ (hl & 7)) << 4),
+                                    make_uint4(ptx::pack_bf16x2(z[0], z[1]), ptx::pack_bf16x2(z[2], z[3]), ptx::pack_bf16x2(z[4], z[5]),
+                                               ptx::pack_bf16x2(z[6], z[7])));
+                    }
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { arrive_leader(&a_ready[stage]); ptx::mbar_arrive(&rs_empty[e_rs]); }
+                    if (++stage == DW2_STAGES) { stage = 0; phase ^= 1; }
+                }
+                meta_n = meta_nn;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) pv[k] = npv[k];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) ev[k] = nev[k];
+            }
+        } else if (kind == 1 && ptid < 32) {
+            // SCALE block: one warp copies the K step's 64 row scales (bf16) into row 0 of the A tile (row 0: no swizzle)
+            int stage = 0; uint32_t phase = 0, it = 0;
+            for (int s = s_beg; s < s_end; ++s)
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int e_rs = it % DW_NRS;
+                    ptx::mbar_wait(&stage_empty[stage], phase ^ 1);
+                    ptx::mbar_wait(&rs_full[e_rs], (it / DW_NRS) & 1);
+                    const float2 x = ptx::lds64f(ptx::smem_u32(rsring) + (uint32_t)e_rs * 256u + (uint32_t)lane * 8u);
+                    ptx::sts32(smem_a + (uint32_t)stage * DW2_STAGE + (uint32_t)lane * 4u, ptx::pack_bf16x2(x.x, x.y));
+                    ptx::fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) { arrive_leader(&a_ready[stage]); ptx::mbar_arrive(&rs_empty[e_rs]); }
+                    if (++stage == DW2_STAGES) { stage = 0; phase ^= 1; }
+                }
+        }
+        // ---- epilogue: this CTA's 128 rows x Nv columns -> accumulated into the split's partial plane (4 warps per lane quarter)
+        if (s_end > s_beg) {
+            { RB_PROF_BEGIN(pf); ptx::mbar_wait(acc_full, 0); RB_PROF_END(pf, pc[1]); }
+            ptx::tc_fence_after();
+            if (kind != 2) {
+                const int qd = warp & 3, hr = hb * 128 + qd * 32 + lane;
+                const bool on = kind == 0 ? hr < p.Hrows : (qd == 0 && lane == 0);      // SCALE block: only TMEM lane 0 carries data (db)
+                float* dst = kind == 0 ? p.dWp + ((size_t)wk.split * p.Hrows + hr) * p.V + v0 : p.dbp + (size_t)wk.split * p.V + v0;
+                if (kind == 0 || qd == 0) {
+                    const int nch = Nv >> 5;
+                    for (int j = q4; j < nch; j += 4) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + (uint32_t)(j * 32), v);
+                        ptx::tmem_ld_wait();
+                        if (on) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                float4* d4 = reinterpret_cast<float4*>(dst + j * 32 + i * 4);
+                                const float4 x = *d4;
+                                *d4 = make_float4(__uint_as_float(v[4 * i]) + x.x, __uint_as_float(v[4 * i + 1]) + x.y,
+                                                  __uint_as_float(v[4 * i + 2]) + x.z, __uint_as_float(v[4 * i + 3]) + x.w);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (pf) {
+        long long* o = p.prof + ((size_t)blockIdx.x * 4 + warp) * 8;
+        o[0] = clock64() - t_start; o[1] = pc[0]; o[2] = pc[1]; o[3] = pc[2]; o[4] = pc[3];
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::cluster_sync();
+    if (warp == 1) ptx::tmem_dealloc2(tmem_base, TC_TMEM_COLS);
+}
+
 }  // namespace rb

@@ -72,7 +72,13 @@ inline int tc_dz_variant() {
     if (v < 0) { const char* e = getenv("RNNTB200_DZ"); v = e ? atoi(e) : 2; if (v != 1 && v != 2) v = 2; }
     return v;
 }
-inline BwdGeom bwd_geometry(int H, int V, int sms = 148, bool dz_pair = true) {
+// dW kernel variant: 2 (default) = CTA pairs (one z block per CTA against 512 columns), 1 = one CTA per (2 blocks x 256 columns)
+inline int tc_dw_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("RNNTB200_DW"); v = e ? atoi(e) : 2; if (v != 1 && v != 2) v = 2; }
+    return v;
+}
+inline BwdGeom bwd_geometry(int H, int V, int sms = 148, bool dz_pair = true, bool dw_pair = true) {
     BwdGeom g{};
     g.ok = false;
     if (H % 64 || V % 64 || H > 768 || H < 64) return g;
@@ -87,13 +93,21 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148, bool dz_pair = true) {
         g.dz_smem = 1024 + (size_t)g.dz_stages * dz_stage + (size_t)(g.NCZ / 32) * 3072 + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
         if (g.dz_smem <= 232448) break;
     }
-    g.dw_smem = 1024 + (size_t)3 * 65536 + 8 * 256 + 512;
     g.nHB = (H + 127) / 128;
     g.nItems = (g.nHB + 2) / 2;               // blocks [0 .. nHB-1, ONES] in pairs
-    g.nVT = (V + 255) / 256;
-    g.S_max = sms / (g.nVT * g.nItems);
-    if (g.S_max < 1) g.S_max = 1;
-    g.dw_grid = g.nVT * g.nItems * g.S_max;
+    if (dw_pair) {                            // a cluster of 2 per (512 columns, item, split): bwd_dw2_kernel
+        g.dw_smem = 1024 + (size_t)4 * 49152 + 8 * 256 + 512;
+        g.nVT = (V + 511) / 512;
+        g.S_max = (sms / 2) / (g.nVT * g.nItems);
+        if (g.S_max < 1) g.S_max = 1;
+        g.dw_grid = 2 * g.nVT * g.nItems * g.S_max;
+    } else {
+        g.dw_smem = 1024 + (size_t)3 * 65536 + 8 * 256 + 512;
+        g.nVT = (V + 255) / 256;
+        g.S_max = sms / (g.nVT * g.nItems);
+        if (g.S_max < 1) g.S_max = 1;
+        g.dw_grid = g.nVT * g.nItems * g.S_max;
+    }
     g.ok = g.dz_smem <= 232448 && g.dw_smem <= 232448;
     return g;
 }
@@ -295,7 +309,7 @@ inline size_t tc_chunk_budget() {
 inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     TcScratch s{};
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
-    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2);
+    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2, tc_dw_variant() == 2);
     const size_t rows_utt = (size_t)g.nTb * g.nUb * 128;
     const size_t per_row = (size_t)d.V * 2 + 8;
     size_t bc = tc_chunk_budget() / (rows_utt * per_row);
@@ -385,7 +399,7 @@ inline long long* tc_prof_buffer(int which) {
 }
 
 inline bool tc_supported(const rnntb200JointDesc& d) {
-    return tc_geometry(d.maxT, d.maxU, d.H, d.V).ok && tc3_geometry(d.H, d.V).ok && bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2).ok;
+    return tc_geometry(d.maxT, d.maxU, d.H, d.V).ok && tc3_geometry(d.H, d.V).ok && bwd_geometry(d.H, d.V, 148, tc_dz_variant() == 2, tc_dw_variant() == 2).ok;
 }
 inline size_t tc_scratch_bytes(const rnntb200JointDesc& d) {
     if (!tc_supported(d)) return 0;
@@ -467,13 +481,14 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
                                 float* db, cudaStream_t s, unsigned* launches) {
     if (!tc_supported(d)) return tc_unsupported(d);
     const TcGeom g = tc_geometry(d.maxT, d.maxU, d.H, d.V);
-    const bool dz_pair = tc_dz_variant() == 2;
-    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, dz_pair);
+    const bool dz_pair = tc_dz_variant() == 2, dw_pair = tc_dw_variant() == 2;
+    const BwdGeom bg = bwd_geometry(d.H, d.V, 148, dz_pair, dw_pair);
     TcScratch sc = tc_scratch_layout(d, scratch);   // Wt / Wb were produced by the forward call
     const bool kept = tc_keep(d, sc);
     if (!tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false, false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true, false>)) ||
         !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<false, true>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dz_kernel<true, true>)) ||
-        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<true>)))
+        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw_kernel<true>)) ||
+        !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw2_kernel<false>)) || !tc_smem_optin(reinterpret_cast<const void*>(bwd_dw2_kernel<true>)))
         return RNNT_STATUS_EXECUTION_FAILED;
     if (cudaMemsetAsync(sc.dWp, 0, sizeof(float) * (size_t)bg.S_max * d.H * d.V, s) != cudaSuccess ||
         cudaMemsetAsync(sc.dbp, 0, sizeof(float) * (size_t)bg.S_max * d.V, s) != cudaSuccess)
@@ -540,9 +555,12 @@ inline rnntStatus_t tc_backward(const rnntb200JointDesc& d, void* scratch, const
                 reinterpret_cast<const float4*>(sc.ppl), xlen, ylen, b0, nb, d.maxU, d.H / 4, reinterpret_cast<float4*>(d_pred));
         }
         {
-            ScopedTimer tmr("bwd_dw_kernel", s);
+            ScopedTimer tmr(dw_pair ? "bwd_dw2_kernel" : "bwd_dw_kernel", s);
             p.prof = prof_dw;
-            if (p.prof) bwd_dw_kernel<true><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
+            if (dw_pair) {
+                if (p.prof) bwd_dw2_kernel<true><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
+                else bwd_dw2_kernel<false><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
+            } else if (p.prof) bwd_dw_kernel<true><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
             else bwd_dw_kernel<false><<<bg.dw_grid, DW_THREADS, bg.dw_smem, s>>>(tm_e64, p);
         }
         *launches += 3;
