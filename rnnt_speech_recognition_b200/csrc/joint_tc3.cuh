@@ -28,7 +28,10 @@
 namespace rb {
 
 constexpr int TC3_THREADS = 480;
-constexpr int TC3_IN_STAGES = 3;
+#ifndef RNNTB200_IN_STAGES
+#define RNNTB200_IN_STAGES 3
+#endif
+constexpr int TC3_IN_STAGES = RNNTB200_IN_STAGES;
 constexpr uint32_t TC3_PRED_BOX = 8 * 128, TC3_ENC_BOX = 16 * 256, TC3_IN_STAGE = 2 * TC3_PRED_BOX + TC3_ENC_BOX;   // 16 x 8 tiles
 constexpr int TC2_NC = 64;             // vocabulary columns per accumulator buffer / W^T chunk
 constexpr int TC2_MAX_STAGES = 24;

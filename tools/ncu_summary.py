@@ -3,6 +3,7 @@ utilisation and occupancy figures quoted in DESIGN.md.  `python tools/ncu_summar
 import csv
 import io
 import json
+import re
 import subprocess
 import sys
 
@@ -49,6 +50,7 @@ def traffic(res, steps):
         short = name.split("(")[0].replace("rb::", "").replace("void ", "").strip()
         # the names bench.py's CUDA-event attribution uses for the two template instances of the forward kernel
         short = short.replace("_kernel<2>", "_kernel<fwd+keep>").replace("_kernel<0>", "_kernel<fwd>")
+        short = re.sub(r"<\s*(true|false|\(bool\)[01])[^>]*>$", "", short)      # bwd_dz_kernel<false, true> -> bwd_dz_kernel
         def num(k):
             v = d.get(k, "0").split()
             x = float(v[0].replace(",", "")) if v else 0.0
