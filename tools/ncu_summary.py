@@ -47,10 +47,13 @@ def traffic(res, steps):
     per, cnt = {}, {}
     for key, d in res.items():
         name = key.split(" #")[0]
-        short = name.split("(")[0].replace("rb::", "").replace("void ", "").strip()
-        # the names bench.py's CUDA-event attribution uses for the two template instances of the forward kernel
-        short = short.replace("_kernel<2>", "_kernel<fwd+keep>").replace("_kernel<0>", "_kernel<fwd>")
-        short = re.sub(r"<\s*(true|false|\(bool\)[01])[^>]*>$", "", short)      # bwd_dz_kernel<false, true> -> bwd_dz_kernel
+        short = name.split("(")[0].replace("rb::", "").replace("void ", "").replace("<unnamed>::", "").strip()
+        # the names bench.py's CUDA-event attribution uses: the forward kernel's two template instances are told apart,
+        # every other kernel drops its template arguments
+        if short.startswith("joint_tc"):
+            short = short.replace("_kernel<2>", "_kernel<fwd+keep>").replace("_kernel<0>", "_kernel<fwd>")
+        else:
+            short = re.sub(r"<[^>]*>$", "", short)
         def num(k):
             v = d.get(k, "0").split()
             x = float(v[0].replace(",", "")) if v else 0.0
@@ -64,6 +67,11 @@ def traffic(res, steps):
 
 
 if __name__ == "__main__":
+    # `--from-json summary.json <steps> traffic.json`: rebuild traffic.json from a summary written earlier (the report itself
+    # is too large to travel back from the GPU box)
+    if sys.argv[1] == "--from-json":
+        json.dump(traffic(json.load(open(sys.argv[2])), int(sys.argv[3])), open(sys.argv[4], "w"), indent=1)
+        sys.exit(0)
     r = main(sys.argv[1])
     if len(sys.argv) >= 4:      # ncu_summary.py X.ncu-rep <steps captured> traffic.json
         json.dump(traffic(r, int(sys.argv[2])), open(sys.argv[3], "w"), indent=1)

@@ -25,7 +25,8 @@ torch.cuda.synchronize()
 L = _lib.load()
 L.rnntb200_debug_prof.restype = C.POINTER(C.c_longlong)
 names = {0: ("bwd_dz_kernel", ["TMA: stage_empty", "MMA: priv_free / stage_full / shared_free", "epilogue warp: acc_full / named barrier"]),
-         1: ("bwd_dw_kernel", ["TMA: stage_empty", "MMA: b_full / a_ready", "producer warp: b_full / acc_full"])}
+         1: ("bwd_dw2_kernel (bwd_dw_kernel with RNNTB200_DW=1)", ["TMA: stage_empty", "MMA: b_full / a_ready", "producer warp: stage_empty / acc_full / rs_full"])}
+# CTA-pair kernels: only the leader's MMA warp works, so the MMA row (an average over all CTAs) shows HALF the leader's numbers
 for which in (0, 1):
     ptr = L.rnntb200_debug_prof(which)
     a = np.ctypeslib.as_array(ptr, shape=(256, 4, 8)).copy()
