@@ -21,9 +21,9 @@
  *
  *  What reaches HBM on the tensor-core path (N = lattice cells, V vocabulary):
  *    keep_activations = 0  forward: lse + two log-probs per cell, alpha, beta (O(N) floats).  The backward
- *                          re-runs the projection per utterance chunk, leaving 2 bytes per logit (fp16 softmax
- *                          numerators) + N*V/8 bytes of running maxima in the workspace for the two gradient
- *                          GEMM kernels to consume; no (B,T,U,V) tensor is produced by the forward call.
+ *                          re-runs the projection per utterance chunk, leaving 2 bytes per logit (bf16 softmax
+ *                          numerators relative to one fp32 reference per lattice row) in the workspace for the two
+ *                          gradient GEMM kernels to consume; no (B,T,U,V) tensor is produced by the forward call.
  *    keep_activations = 1  the forward itself writes those numerators (one pass fewer on the tensor cores).
  *    In both modes the logit gradients, dZ and z = tanh(enc+pred) exist only in shared / tensor memory.
  *
@@ -151,7 +151,7 @@ typedef struct {
     int allow_host_sync;
     /** 0: nothing but lse / log-prob pairs / alpha / beta survives the forward; the backward re-runs the projection
      *  chunk by chunk.  1 (tensor-core path): the forward also leaves, in the workspace, the softmax numerators of
-     *  every lattice cell as fp16 (2 bytes per logit) and their running maxima; the backward then skips its own
+     *  every lattice cell as bf16 (2 bytes per logit) and one fp32 reference per lattice row; the backward then skips its own
      *  projection pass.  Set it when a backward call will follow; it is honoured only when the whole batch fits one
      *  workspace chunk (<= 16 GiB of numerators), otherwise (and for fp32) ignored.  Must have the same value in the
      *  forward and the backward call. */
