@@ -29,6 +29,11 @@ inline Tc2Geom tc4_geometry(int H, int V) {
     return g;
 }
 
+#ifndef RNNTB200_TC4_PRE
+#define RNNTB200_TC4_PRE 4
+#endif
+constexpr int TC4_PRE = RNNTB200_TC4_PRE;      // K blocks of the next tile's z produced into registers ahead of z_free
+
 template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) joint_tc4_kernel(const __grid_constant__ CUtensorMap tmap_wt,
                                                                    const __grid_constant__ CUtensorMap tmap_pred,
@@ -231,12 +236,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
             const TileInfo ti = decode_tile(p, tile);
             const int tl = r2 / p.UU, ul = r2 % p.UU;   // row of the enc box / of the pred box
             const bool ok = (ti.t0 + tl) < ti.Tn && (ti.u0 + ul) < ti.Un;
-            for (int kb = 0; kb < KB; ++kb) {
+            // one K block of z: this thread's 32 columns (k-half hh) of its lattice row, tanh -> fp16 pairs
+            auto produce = [&](uint32_t (&zr)[16]) {
                 ptx::mbar_wait(&in_full[st], ph);
                 const uint32_t base = insm_a + (uint32_t)st * IN_STAGE;
                 const uint32_t prow = base + (uint32_t)hh * TC3_PRED_BOX + (uint32_t)(ul * 128);      // SW128: chunk c at (c ^ (row & 7)) * 16
                 const uint32_t erow = base + 2 * TC3_PRED_BOX + (uint32_t)(tl * 256 + hh * 128);       // plain layout
-                uint32_t zr[16];
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float4 q = ptx::lds128f(prow + (uint32_t)((c ^ (ul & 7)) << 4));
@@ -254,12 +259,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&in_empty[st]);                       // this warp is done with the stage
                 if (++st == TC3_IN_STAGES) { st = 0; ph ^= 1; }
-                if (kb == 0) ptx::mbar_wait(z_free, (it & 1) ^ 1);   // previous tile's MMAs have retired: z columns reusable
+            };
+            auto publish = [&](int kb, const uint32_t (&zr)[16]) {
                 ptx::tmem_st_32x16(tmem_base + ((uint32_t)(q4 * 32) << 16) + (uint32_t)(kb * 32 + hh * 16), zr);
                 ptx::tmem_st_wait();
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) arrive_leader(&z_full[kb]);
+            };
+            // z is single-buffered in tensor memory: its columns are free only when the previous tile's MMAs have retired
+            // (z_free).  The first TC4_PRE K blocks of the tile are produced into REGISTERS while those MMAs still run, so
+            // that after z_free only KB - TC4_PRE blocks remain on the tile's critical path.
+            uint32_t zp[TC4_PRE][16];
+            const int npre = KB < TC4_PRE ? KB : TC4_PRE;
+#pragma unroll
+            for (int i = 0; i < TC4_PRE; ++i)
+                if (i < npre) produce(zp[i]);
+            ptx::mbar_wait(z_free, (it & 1) ^ 1);
+#pragma unroll
+            for (int i = 0; i < TC4_PRE; ++i)
+                if (i < npre) publish(i, zp[i]);
+            for (int kb = npre; kb < KB; ++kb) {
+                uint32_t zr[16];
+                produce(zr);
+                publish(kb, zr);
             }
             ++it;
         }
@@ -303,49 +326,65 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
                     ptx::tmem_ld_wait();
                     if (p.dbg & 1) { s += __uint_as_float(v[0]); continue; }
                     const int col0 = c * NC + j * 32;
-                    const float bv = bias_in_smem ? __uint_as_float(ptx::lds32(bias_a + (uint32_t)((col0 + lane) * 4)))
-                                                  : __ldg(p.bias + col0 + lane) * LOG2E;
                     float y[32];
+                    if (bias_in_smem) {
+                        // the 32 biases of the group (pre-scaled by log2 e) as 8 broadcast 16-byte shared-memory loads -- one
+                        // wavefront each -- instead of one load and 32 shuffles
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
+                        for (int i = 0; i < 8; ++i) {
+                            const float4 b4 = ptx::lds128f(bias_a + (uint32_t)((col0 + 4 * i) * 4));
+                            y[4 * i] = fmaf(__uint_as_float(v[4 * i]), LOG2E, b4.x); y[4 * i + 1] = fmaf(__uint_as_float(v[4 * i + 1]), LOG2E, b4.y);
+                            y[4 * i + 2] = fmaf(__uint_as_float(v[4 * i + 2]), LOG2E, b4.z); y[4 * i + 3] = fmaf(__uint_as_float(v[4 * i + 3]), LOG2E, b4.w);
+                        }
+                    } else {
+                        const float bv = __ldg(p.bias + col0 + lane) * LOG2E;
+#pragma unroll
+                        for (int i = 0; i < 32; ++i)
+                            y[i] = fmaf(__uint_as_float(v[i]), LOG2E, __shfl_sync(0xffffffffu, bv, i));
+                    }
                     {
-                        float gm = y[0];
+                        // The row sum is kept as (m2, s): sum = s * 2^m2.  m2 starts as the row's FIXED reference (the maximum of its
+                        // first 32 logits) and stays there unless a later logit exceeds ref + 100 (detected on the group's sum, no
+                        // running maximum is computed in the common path).  Both modes use the same arithmetic, hence identical costs
+                        // whether or not the numerators are kept.  MODE 2 stores the numerators 2^(y - ref) (bf16).
+                        if (col0 == 0) {
+                            float gm = y[0];
 #pragma unroll
-                        for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
-                        const float mn = fmaxf(m2, gm);
-                        float acc = 0.f;
-                        // Both modes form the group's sum from 2^(y - ref) against the row's FIXED reference (the maximum of its first 32
-                        // logits), rescaled once per group into the running-maximum frame: identical arithmetic, hence identical costs,
-                        // whether or not the numerators are kept.  MODE 2 stores those numerators (bf16).
-                        if (col0 == 0) ref = gm;
+                            for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
+                            ref = gm; m2 = gm;
+                        }
                         uint32_t o[16];
-                        if (gm - ref <= 100.f) {
-                            float accr = 0.f;
+                        float accr = 0.f;
 #pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                const float e0 = ptx::ex2_approx(y[i] - ref), e1 = ptx::ex2_approx(y[i + 1] - ref);
-                                accr += e0 + e1;
-                                if (MODE == 2) o[i >> 1] = ptx::pack_bf16x2(e0, e1);
-                            }
-                            acc = accr * ptx::ex2_approx(ref - mn);
+                        for (int i = 0; i < 32; i += 2) {
+                            const float e0 = ptx::ex2_approx(y[i] - ref), e1 = ptx::ex2_approx(y[i + 1] - ref);
+                            accr += e0 + e1;
+                            if (MODE == 2) o[i >> 1] = ptx::pack_bf16x2(e0, e1);
+                        }
+                        if (accr < 1.0e30f) {            // every term below 2^100 (NaN / inf fail the test)
+                            s += (m2 == ref) ? accr : accr * ptx::ex2_approx(ref - m2);
                         } else {
-                            // a logit more than 2^100 above the reference (never seen outside adversarial inputs): the sum is taken
-                            // against the running maximum, the stored values are clamped at 2^100
+                            // a logit about 2^100 above the reference (never seen outside adversarial inputs): the group's sum is
+                            // taken against its own maximum and the row switches to that frame; stored values are clamped at 2^100
+                            float gm = y[0];
+#pragma unroll
+                            for (int i = 1; i < 32; ++i) gm = fmaxf(gm, y[i]);
+                            const float mn = fmaxf(m2, gm);
+                            float acc = 0.f;
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) {
                                 acc += ptx::ex2_approx(y[i] - mn) + ptx::ex2_approx(y[i + 1] - mn);
                                 if (MODE == 2)
                                     o[i >> 1] = ptx::pack_bf16x2(ptx::ex2_approx(fminf(y[i] - ref, 100.f)), ptx::ex2_approx(fminf(y[i + 1] - ref, 100.f)));
                             }
+                            s = s * ptx::ex2_approx(m2 - mn) + acc;
+                            m2 = mn;
                         }
                         if (MODE == 2) {
                             __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
                             ptx::st_global_256(dst, o);
                             ptx::st_global_256(dst + 16, o + 8);
                         }
-                        s = s * ptx::ex2_approx(m2 - mn) + acc;
-                        m2 = mn;
                         if (p.blank >= col0 && p.blank < col0 + 32) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
