@@ -143,6 +143,9 @@ def cpu_reference_runner(cfg):
     torch.set_num_threads(cores)
     B, T, U, V, H = (cfg[k] for k in "BTUVH")
     d = synth(cfg, 1234, "cpu")
+    # micro-batch of the CPU arm: 4 utterances unless their (mb,T,U,V) fp32 slabs -- logits, log-probs,
+    # gradients and their autograd copies -- would not fit a host comfortably (C5: 5.2 GB per utterance and slab)
+    mb_default = max(1, min(4, int(6e9 // (4.0 * T * U * V))))
     if oracle.have_ref():
         class RefLoss(torch.autograd.Function):
             @staticmethod
@@ -155,7 +158,7 @@ def cpu_reference_runner(cfg):
             def backward(ctx, go):
                 return ctx.grads.mul_(go.view(-1, 1, 1, 1)), None, None, None
 
-        def run(n, mb=4):
+        def run(n, mb=mb_default):
             # micro-batches of `mb` utterances: utterances are independent (cpu_rnnt.h:290-301) and
             # warp-transducer's OpenMP loop parallelises over the minibatch only, so a micro-batch gives it work while the
             # (mb,T,U,V) slabs stay a few GB
@@ -169,24 +172,24 @@ def cpu_reference_runner(cfg):
                 c = RefLoss.apply(lp, d["labels"][j].numpy(), d["il"][j].numpy(), d["ll"][j].numpy())
                 (c.sum() / B).backward()
             return time.perf_counter() - t0
-        return run, "reference", cores, ("oracle/_ref/libwarprnnt.so (unmodified reference, OpenMP over the micro-batch) + "
-                                         "torch-CPU fp32 joint/autograd, micro-batches of 4 utterances")
+        return run, "reference", cores, mb_default, ("oracle/_ref/libwarprnnt.so (unmodified reference, OpenMP over the micro-batch) + "
+                                                     "torch-CPU fp32 joint/autograd, micro-batches of %d utterance(s)" % mb_default)
 
     a = {k: v.numpy() for k, v in d.items()}
 
-    def run(n, mb=4):
+    def run(n, mb=mb_default):
         t0 = time.perf_counter()
         idx = [i % B for i in range(n)]
         oracle.joint_loss_grad(a["enc"][idx], a["pred"][idx], a["W"], a["b"], a["labels"][idx], a["il"][idx],
                                a["ll"][idx], grad_scale=np.full(n, 1.0 / B, np.float32))
         return time.perf_counter() - t0
-    return run, "port", cores, "oracle/rnnt_oracle.c (C restatement, OpenMP)"
+    return run, "port", cores, mb_default, "oracle/rnnt_oracle.c (C restatement, OpenMP)"
 
 
 def cpu_baseline(cfg, budget_s=20.0):
-    run, kind, cores, note = cpu_reference_runner(cfg)
+    run, kind, cores, mb, note = cpu_reference_runner(cfg)
     t1 = run(1)                                     # warm-up + calibration
-    n = max(1, min(cfg["B"], 4 * max(1, int(budget_s / 3 / max(4 * t1, 1e-3)))))     # whole micro-batches of 4
+    n = max(1, min(cfg["B"], mb * max(1, int(budget_s / 3 / max(mb * t1, 1e-3)))))   # whole micro-batches
     reps = max(1, min(3, int(budget_s / max(n * t1, 1e-3))))
     ts = [run(n) for _ in range(reps)]              # best of up to 3
     t = min(ts)
@@ -197,12 +200,12 @@ def cpu_baseline(cfg, budget_s=20.0):
 def reference_arm(args, cfg, rank):
     if rank != 0:
         return
-    run, kind, cores, note = cpu_reference_runner(cfg)
+    run, kind, cores, mb, note = cpu_reference_runner(cfg)
     t1 = run(1)
     total = args.steps + args.warmup
     n = max(1, min(cfg["B"], int(150.0 / (total * max(t1, 1e-3)))))
-    if n >= 4:
-        n -= n % 4                                  # whole micro-batches of 4 utterances
+    if n >= mb:
+        n -= n % mb                                 # whole micro-batches
     for _ in range(args.warmup):
         run(n)
     times = [run(n) for _ in range(args.steps)]
