@@ -28,7 +28,14 @@
 namespace rb {
 
 constexpr int BW_TT = 16, BW_UU = 8;
-constexpr int DZ_THREADS = 352;      // warp 0 operand TMA | 1 MMA | 2-9 epilogue | 10 enc/pred TMA for the epilogue
+#ifndef RNNTB200_DZ_EG
+#define RNNTB200_DZ_EG 4
+#endif
+constexpr int DZ_EG = RNNTB200_DZ_EG;                 // epilogue warp groups (one warp per TMEM lane quarter each): chunk c belongs to group c % DZ_EG
+constexpr int DZ_EPI_WARPS = 4 * DZ_EG;
+constexpr int DZ_MAXJ = (12 + DZ_EG - 1) / DZ_EG;     // 32-column chunks per warp and unit (NCZ <= 384)
+constexpr int DZ_TMA2_WARP = 2 + DZ_EPI_WARPS;        // enc / pred TMA for the epilogue
+constexpr int DZ_THREADS = 32 * (3 + DZ_EPI_WARPS);   // warp 0 operand TMA | 1 MMA | 2.. epilogue | last: enc/pred TMA for the epilogue
 constexpr int DZ_MAX_STAGES = 6;
 constexpr int DW_THREADS = 576;      // warp 0 TMA | 1 MMA | 2-17 z producers, then epilogue (16 warps: the tanh chain is latency-bound at 2 warps per scheduler)
 constexpr int DW_STAGES = 3;
@@ -103,7 +110,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     uint8_t* encb = predb + (size_t)nch * 1024;                            // [nch][16 x 128 B]
     uint8_t* dpb = encb + (size_t)nch * 2048;                              // [hh][buf][4][8][36] floats
     constexpr int DP_ONE = 4 * 8 * 36;                                     // floats per (hh, buf)
-    uint64_t* bars = reinterpret_cast<uint64_t*>(dpb + 2 * 2 * DP_ONE * 4);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dpb + DZ_EG * 2 * DP_ONE * 4);
     uint64_t* stage_full = bars;                         // [stages] TMA -> MMA
     uint64_t* stage_empty = stage_full + DZ_MAX_STAGES;  // [stages] MMA -> TMA
     uint64_t* acc_full = stage_empty + DZ_MAX_STAGES;    // [2] MMA -> epilogue (unit parity)
@@ -116,9 +123,9 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         for (int i = 0; i < DZ_MAX_STAGES; ++i) { ptx::mbar_init(&stage_full[i], 1); ptx::mbar_init(&stage_empty[i], 1); }
-        ptx::mbar_init(epi_full, 1); ptx::mbar_init(epi_empty, 8);
-        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], PAIR ? 16 : 8); }
-        ptx::mbar_init(shared_free, PAIR ? 16 : 8);
+        ptx::mbar_init(epi_full, 1); ptx::mbar_init(epi_empty, DZ_EPI_WARPS);
+        for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&priv_free[i], (PAIR ? 2 : 1) * DZ_EPI_WARPS); }
+        ptx::mbar_init(shared_free, (PAIR ? 2 : 1) * DZ_EPI_WARPS);
         ptx::fence_barrier_init();
     }
     if (warp == 1) {
@@ -126,7 +133,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         else { ptx::tmem_alloc(tmem_ptr, TC_TMEM_COLS); ptx::tmem_relinquish(); }
     }
     if (warp == 0 && lane == 0) { ptx::prefetch_tmap(&tmap_e); ptx::prefetch_tmap(&tmap_wp); ptx::prefetch_tmap(&tmap_ws); }
-    if (warp == 10 && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
+    if (warp == DZ_TMA2_WARP && lane == 0) { ptx::prefetch_tmap(&tmap_pred); ptx::prefetch_tmap(&tmap_enc); }
     ptx::tc_fence_before();
     __syncthreads();
     if (PAIR) ptx::cluster_sync();       // the peer's barriers exist before anyone arrives on them remotely
@@ -233,7 +240,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     }
                 }
         }
-    } else if (warp == 10) {
+    } else if (warp == DZ_TMA2_WARP) {
         // ===================== enc / pred TMA for the epilogue: one unit ahead of it =====================
         if (lane == 0) {
             uint32_t uq = 0;
@@ -258,7 +265,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         const int qd = warp & 3, hh = (warp - 2) >> 2, qslot = (warp - 2) & 3;
         const int r = qd * 32 + lane, ul = lane & 7;
         const int npr = priv >> 5, nsh = sh >> 5;                  // 32-column chunks of the private / shared zone
-        const int nsh_h = nsh >> 1, npr_h = (npr - hh + 1) >> 1;   // this warp's share (chunks with index % 2 == hh)
+        const int nsh_h = (nsh - hh + DZ_EG - 1) / DZ_EG, npr_h = (npr - hh + DZ_EG - 1) / DZ_EG;   // this warp's share (chunks with index % DZ_EG == hh)
         const int nj = nsh_h + npr_h;
         const uint32_t dp0 = ptx::smem_u32(dpb) + (uint32_t)hh * 2 * DP_ONE * 4;
         const int off4 = (ul & 1) * 16 + ((ul >> 1) & 1) * 8 + ((ul >> 2) & 1) * 4;   // columns this lane keeps after the u butterfly
@@ -271,11 +278,11 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
             if (tb * BW_TT >= Tn) continue;
             const int nub = (Un + BW_UU - 1) / BW_UU;
             const int t = tb * BW_TT + (r >> 3);
-            float accE[2][6][4];
+            float accE[2][DZ_MAXJ][4];
 #pragma unroll
             for (int a = 0; a < 2; ++a)
 #pragma unroll
-                for (int j = 0; j < 6; ++j)
+                for (int j = 0; j < DZ_MAXJ; ++j)
 #pragma unroll
                     for (int i = 0; i < 4; ++i) accE[a][j][i] = 0.f;
             const int nq = PAIR ? (nub + 1) >> 1 : nub;
@@ -289,7 +296,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                         ptx::tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if (nsh_h > 0) arrive_leader(shared_free);
+                            if (sh) arrive_leader(shared_free);
                             arrive_leader(&priv_free[q & 1]);
                         }
                     }
@@ -306,9 +313,17 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     { RB_PROF_BEGIN(pf); ptx::mbar_wait(epi_full, eq & 1); RB_PROF_END(pf, pc[2]); }
                     const int n0 = pass * NCZ;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
+                    if ((sh && nsh_h == 0) || nj == 0) {       // no chunk of the shared zone / of the unit falls to this warp (narrow H)
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (sh && nsh_h == 0) arrive_leader(shared_free);
+                            if (nj == 0) arrive_leader(&priv_free[par]);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < DZ_MAXJ; ++j) {
                         if (j >= nj) continue;
-                        const int c = j < nsh_h ? npr + 2 * j + hh : 2 * (j - nsh_h) + hh;      // chunk of this pass's NCZ columns
+                        const int c = j < nsh_h ? npr + DZ_EG * j + hh : DZ_EG * (j - nsh_h) + hh;      // chunk of this pass's NCZ columns
                         const uint32_t col = c < npr ? (par ? (uint32_t)p.odd_base : 0u) + 32u * c : 32u * c;
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + col, v);
@@ -400,9 +415,9 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass >= NP) continue;
 #pragma unroll
-                    for (int j = 0; j < 6; ++j) {
+                    for (int j = 0; j < DZ_MAXJ; ++j) {
                         if (j >= nj) continue;
-                        const int c = j < nsh_h ? npr + 2 * j + hh : 2 * (j - nsh_h) + hh;
+                        const int c = j < nsh_h ? npr + DZ_EG * j + hh : DZ_EG * (j - nsh_h) + hh;
                         const float4 v4 = make_float4(accE[pass][j][0], accE[pass][j][1], accE[pass][j][2], accE[pass][j][3]);
                         if (PAIR) atomicAdd(reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4), v4);    // the two CTAs' halves of the run
                         else *reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4) = v4;

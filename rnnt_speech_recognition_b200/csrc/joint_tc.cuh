@@ -66,6 +66,10 @@ struct BwdGeom {
     int nVT, nHB, nItems, S_max, dw_grid;     // S_max = the split count S
     bool ok;
 };
+#ifndef RNNTB200_DZ_EG
+#define RNNTB200_DZ_EG 4
+#endif
+constexpr int RB_DZ_EG = RNNTB200_DZ_EG;      // epilogue warp groups of the dZ kernel (bwd_tc.cuh: DZ_EG)
 // dZ kernel variant: 2 (default) = CTA pairs (cta_group::2, one copy of each W stage per two tiles), 1 = one CTA per tile
 inline int tc_dz_variant() {
     static int v = -1;
@@ -90,7 +94,7 @@ inline BwdGeom bwd_geometry(int H, int V, int sms = 148, bool dz_pair = true, bo
     // operand stage: the tile's E' block (16 KB) + the W rows this CTA loads (all NCZ of the pass, or half of them in a pair)
     const size_t dz_stage = 16384 + (size_t)(dz_pair ? g.NCZ / 2 : g.NCZ) * 128;
     for (g.dz_stages = dz_pair ? 6 : 3; g.dz_stages >= 2; --g.dz_stages) {
-        g.dz_smem = 1024 + (size_t)g.dz_stages * dz_stage + (size_t)(g.NCZ / 32) * 3072 + (size_t)2 * 2 * 4 * 8 * 36 * 4 + 512;
+        g.dz_smem = 1024 + (size_t)g.dz_stages * dz_stage + (size_t)(g.NCZ / 32) * 3072 + (size_t)RB_DZ_EG * 2 * 4 * 8 * 36 * 4 + 512;
         if (g.dz_smem <= 232448) break;
     }
     g.nHB = (H + 127) / 128;
