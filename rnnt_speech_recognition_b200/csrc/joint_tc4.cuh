@@ -296,6 +296,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
         }
     } else if (warp < 4) {
         // ===================== epilogue warps 0-3: thread = lattice cell (TMEM lane) =====================
+        // (Eight epilogue warps -- two per lattice row, each taking one 32-column half of every chunk and combining their row
+        //  states through shared memory -- were measured: 2.80 vs 2.71 ms in keep mode, 2.54 vs 2.54 without.  The epilogue is
+        //  not short of warps; the 0.34 ms it costs comes from sharing the MUFU / issue slots with the producers.)
         constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
         const uint32_t bias_a = ptx::smem_u32(bias2);
         uint32_t g = 0;
