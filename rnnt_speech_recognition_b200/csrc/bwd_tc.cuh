@@ -265,8 +265,10 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
         const int qd = warp & 3, hh = (warp - 2) >> 2, qslot = (warp - 2) & 3;
         const int r = qd * 32 + lane, ul = lane & 7;
         const int npr = priv >> 5, nsh = sh >> 5;                  // 32-column chunks of the private / shared zone
-        const int nsh_h = (nsh - hh + DZ_EG - 1) / DZ_EG, npr_h = (npr - hh + DZ_EG - 1) / DZ_EG;   // this warp's share (chunks with index % DZ_EG == hh)
-        const int nj = nsh_h + npr_h;
+        // The unit's chunks in processing order -- shared zone first, then the private zone -- are dealt round-robin to the
+        // DZ_EG groups: group hh takes positions hh, hh + DZ_EG, ...  (at most DZ_MAXJ = ceil(12 / DZ_EG) of them).
+        const int nsh_h = (nsh - hh + DZ_EG - 1) / DZ_EG;           // how many of this warp's positions lie in the shared zone
+        const int nj = (npr + nsh - hh + DZ_EG - 1) / DZ_EG;
         const uint32_t dp0 = ptx::smem_u32(dpb) + (uint32_t)hh * 2 * DP_ONE * 4;
         const int off4 = (ul & 1) * 16 + ((ul >> 1) & 1) * 8 + ((ul >> 2) & 1) * 4;   // columns this lane keeps after the u butterfly
         const int cbase = ((lane >> 3) & 1) * 16 + ((lane >> 4) & 1) * 8;              // ... after the t butterfly
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < DZ_MAXJ; ++j) {
                         if (j >= nj) continue;
-                        const int c = j < nsh_h ? npr + DZ_EG * j + hh : DZ_EG * (j - nsh_h) + hh;      // chunk of this pass's NCZ columns
+                        const int pos = hh + DZ_EG * j, c = pos < nsh ? npr + pos : pos - nsh;      // chunk of this pass's NCZ columns
                         const uint32_t col = c < npr ? (par ? (uint32_t)p.odd_base : 0u) + 32u * c : 32u * c;
                         uint32_t v[32];
                         ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + col, v);
@@ -417,7 +419,7 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
 #pragma unroll
                     for (int j = 0; j < DZ_MAXJ; ++j) {
                         if (j >= nj) continue;
-                        const int c = j < nsh_h ? npr + DZ_EG * j + hh : DZ_EG * (j - nsh_h) + hh;
+                        const int pos = hh + DZ_EG * j, c = pos < nsh ? npr + pos : pos - nsh;
                         const float4 v4 = make_float4(accE[pass][j][0], accE[pass][j][1], accE[pass][j][2], accE[pass][j][3]);
                         if (PAIR) atomicAdd(reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4), v4);    // the two CTAs' halves of the run
                         else *reinterpret_cast<float4*>(drow + pass * NCZ + 32 * c + off4) = v4;

@@ -32,6 +32,14 @@ def oracle_of(oracle, k, gs, blank=0):
     (1, 9, 140, 64, 64, 3, False),       # U > 128: 18 u-blocks per t-block
     (2, 33, 128, 512, 640, 4, True),     # H = 640: two dZ passes, double + single dW items, two v-tiles
     (2, 40, 24, 320, 768, 6, True),      # H = 768 (largest supported), V = 320: a 64-wide last v-tile
+    # every accumulator plan of the dZ kernel and every block-slot layout of the dW kernel (H), partial last v-tiles (V)
+    (2, 24, 12, 576, 256, 7, True),      # H = 256: one pass, no shared zone; dW blocks [0, 1, SCALE]: a (SCALE, empty) pair; V = 512 + 64
+    (1, 20, 10, 1088, 512, 8, False),    # H = 512: two passes of 256 columns; three dW v-tiles (512, 512, 64)
+    (2, 18, 9, 128, 448, 9, True),       # H = 448: two passes of 224 columns (7 chunks over 4 epilogue groups)
+    (2, 18, 9, 256, 576, 10, True),      # H = 576: shared zone of 64 columns -- two epilogue groups own no shared chunk
+    (1, 17, 20, 192, 384, 11, False),    # H = 384: one pass, shared zone of 256 columns, private 128
+    (2, 10, 5, 64, 192, 12, True),       # H = 192: six chunks, 1.5 dW blocks
+    (1, 16, 8, 640, 704, 13, False),     # H = 704: two passes of 352 columns, shared zone 192
 ])
 @pytest.mark.parametrize("keep", [True, False])   # backward from the kept numerators / after re-running the projection
 def test_tc_vs_oracle(oracle, B, T, U, V, H, seed, ragged, keep):
