@@ -46,9 +46,10 @@ __device__ __forceinline__ T log_sum_exp(T a, T b) {
 // throughput) sets the kernel time.  max + log2(1 + 2^(-|a-b|*log2 e)) * ln 2 on the MUFU ex2/lg2 units is ~3x
 // shorter than log1pf(expf(.)) and agrees with it to a few ulp (|error| < 3e-7 per step, far inside rtol 1e-4).
 __device__ __forceinline__ float log_sum_exp_fast(float a, float b) {
-    if (a == -CUDART_INF_F) return b;
-    if (b == -CUDART_INF_F) return a;
-    const float mx = fmaxf(a, b), d = -fabsf(a - b);
+    // branch-free (the chain's latency is what counts): with one argument -inf the exponential is 0 and the result the other
+    // argument, bit for bit (lg2(1) = 0); with both -inf the difference is forced to 0 and the result is -inf + ln 2 = -inf
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    const float d = (mx == -CUDART_INF_F) ? 0.f : mn - mx;
     float e, l;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(d * 1.4426950408889634f));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
@@ -222,95 +223,111 @@ __global__ void __launch_bounds__(256) rnnt_grad_vec_kernel(const float* logits,
 // alpha / beta wavefronts.  grid = (B, 2): blockIdx.y == 0 runs alpha, 1 runs beta, so the two
 // recurrences of one utterance overlap on different SMs.  Thread u owns lattice column u and
 // walks the anti-diagonals n = t+u; its own previous value stays in a register, the neighbour's
-// arrives by warp shuffle (and through a 2-slot shared-memory mailbox across warp boundaries,
-// one __syncthreads per step only when maxU > 32).  The two cached log-probs of the thread's OWN
+// arrives by warp shuffle; across warp boundaries through a shared-memory ring, with the warps running skewed
+// by PF steps so that ONE __syncthreads per PF steps suffices (none when maxU <= 32).  The two cached log-probs of the thread's OWN
 // cell are the only global reads: row n of the skewed planes, fully coalesced, software-prefetched
 // PF rows ahead because they do not depend on the recurrence.
 //   alpha(t,u) = LSE(alpha(t-1,u)+lpb(t-1,u), alpha(t,u-1)+lpl(t,u-1))        cpu_rnnt.h:182-195
 //   beta(t,u)  = LSE(beta(t+1,u)+lpb(t,u),    beta(t,u+1)+lpl(t,u))            cpu_rnnt.h:223-236
 //   llForward  = alpha(T-1,U-1)+lpb(T-1,U-1); llBackward = beta(0,0)           cpu_rnnt.h:209,251
 // ---------------------------------------------------------------------------------------------
+template <typename T, int PF, bool BETA>
+__device__ __forceinline__ void alpha_beta_body(const T* __restrict__ lpb, const T* __restrict__ lpl, T* __restrict__ out,
+                                                T* __restrict__ ll, const int* __restrict__ xlen,
+                                                const int* __restrict__ ylen, int maxU, long long SK) {
+    const int b = blockIdx.x;
+    const int u = threadIdx.x, lane = u & 31, warp = u >> 5;
+    const int Tn = xlen[b], Un = ylen[b] + 1;
+    const int nsteps = Tn + Un - 1;
+    const int nwarps_blk = (int)(blockDim.x >> 5);
+    const int nwarps = min(nwarps_blk, (Un + 31) >> 5);       // warps that own a column of THIS utterance
+    const bool multi = nwarps_blk > 1;
+    const bool col_ok = u < Un;
+    // Cross-warp hand-over WITHOUT a barrier per step: the warps run SKEWED by PF steps -- warp w (alpha; mirrored for beta)
+    // executes step i during macro iteration i / PF + w -- so everything a warp needs from its neighbour during a macro
+    // iteration (the neighbour's edge-lane value of the PREVIOUS step, for each of its PF steps) was produced at least one
+    // macro iteration earlier.  One __syncthreads per PF steps instead of one per step; the pipeline fill costs
+    // (nwarps - 1) * PF extra steps.  Within a warp the anti-diagonal dependency is a shuffle.  The step itself is kept
+    // free of branches, divisions and 64-bit multiplies: ONE warp per scheduler runs a chain of T+U-1 dependent steps, so
+    // every instruction on it is latency (measured before: ~100 instructions and a dozen branches per step, 270 ns).
+    constexpr int RING = 4 * PF;                      // edge values of the last 4 macro iterations per warp (power of two)
+    static_assert((RING & (RING - 1)) == 0, "ring index is masked");
+    __shared__ T mailbox[32][RING];
+
+    const long long base = (long long)b * SK + u;
+    const T NEG = neg_inf<T>();
+    T own = NEG;     // alpha: alpha(t-1,u)+lpb(t-1,u)   beta: beta(t+1,u)
+    T pass = NEG;    // alpha: alpha(t,u)+lpl(t,u)       beta: beta(t,u)   (handed to the neighbour)
+    T result = 0;
+
+    const int lag = (multi && warp < nwarps) ? (BETA ? nwarps - 1 - warp : warp) * PF : 0;   // this warp runs `lag` steps behind the first one
+    const int src = BETA ? warp + 1 : warp - 1;                                  // neighbour warp whose edge lane feeds this one
+    const bool has_src = BETA ? (warp + 1 < nwarps) : (warp > 0);
+    const bool edge_in = lane == (BETA ? 31 : 0), edge_out = multi && lane == (BETA ? 0 : 31);
+    const int nmacro = (nsteps + PF - 1) / PF + (multi ? nwarps - 1 : 0);
+    // step i works on diagonal n = i (alpha) / nsteps - 1 - i (beta): row n of the skewed planes, one pointer bump per step
+    const long long dstep = BETA ? -(long long)maxU : (long long)maxU;
+    T cb[PF], cl[PF], nb[PF], nl[PF];
+    auto fetch = [&](int i0, T* vb, T* vl) {
+#pragma unroll
+        for (int j = 0; j < PF; ++j) {
+            const int i = i0 + j;
+            const bool ok = col_ok && i >= 0 && i < nsteps;
+            const long long off = base + (long long)(ok ? (BETA ? nsteps - 1 - i : i) : 0) * maxU;
+            vb[j] = ok ? lpb[off] : T(0);
+            vl[j] = ok ? lpl[off] : T(0);
+        }
+    };
+    fetch(-lag, nb, nl);
+    for (int m = 0; m < nmacro; ++m) {
+        const int i0 = m * PF - lag;
+#pragma unroll
+        for (int j = 0; j < PF; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
+        fetch(i0 + PF, nb, nl);
+        T* po = out + base + (long long)(BETA ? nsteps - 1 - i0 : i0) * maxU;     // row of step i0 (dereferenced only when in range)
+        int t = (BETA ? nsteps - 1 - i0 : i0) - u;                                 // time index of this thread's cell at step i0
+#pragma unroll
+        for (int j = 0; j < PF; ++j, po += dstep, t += BETA ? -1 : 1) {
+            const int i = i0 + j;
+            if (i >= 0 && i < nsteps) {  // uniform across the warp
+                T nbr = BETA ? __shfl_down_sync(0xffffffffu, pass, 1) : __shfl_up_sync(0xffffffffu, pass, 1);
+                if (edge_in)      // the neighbour warp's edge value of step i - 1 (nothing before step 0)
+                    nbr = (has_src && i > 0) ? mailbox[src][(i - 1) & (RING - 1)] : NEG;
+                const bool active = col_ok && t >= 0 && t < Tn;
+                const T vb = cb[j], vl = cl[j];
+                T val;
+                if (!BETA) {
+                    // alpha(t,u); own == -inf when t == 0, nbr is unused (forced -inf) when u == 0
+                    const T emit = (u > 0) ? nbr : NEG;
+                    val = (i == 0) ? T(0) : wave_lse(emit, own);
+                } else {
+                    const T no_emit = (t < Tn - 1) ? own + vb : NEG;
+                    const T emit = (u < Un - 1) ? nbr + vl : NEG;
+                    val = (t == Tn - 1 && u == Un - 1) ? vb : wave_lse(emit, no_emit);
+                }
+                if (active) {
+                    *po = val;
+                    own = BETA ? val : val + vb;
+                    pass = BETA ? val : val + vl;
+                    result = own;      // alpha, last cell: alpha(T-1,U-1)+lpb(T-1,U-1);  beta, cell (0,0): beta(0,0)
+                }
+                if (edge_out) mailbox[warp][i & (RING - 1)] = pass;
+            }
+        }
+        if (multi) __syncthreads();
+    }
+    if (!BETA && u == Un - 1) ll[b] = result;
+    if (BETA && u == 0) ll[b] = result;
+}
+
 template <typename T, int PF>
 __global__ void __launch_bounds__(1024) alpha_beta_kernel(const T* __restrict__ lpb, const T* __restrict__ lpl,
                                                           T* __restrict__ alphas, T* __restrict__ betas,
                                                           T* __restrict__ llf, T* __restrict__ llb,
                                                           const int* __restrict__ xlen,
                                                           const int* __restrict__ ylen, int maxU, long long SK) {
-    const int b = blockIdx.x;
-    const bool is_beta = blockIdx.y == 1;
-    const int u = threadIdx.x, lane = u & 31, warp = u >> 5;
-    const int Tn = xlen[b], Un = ylen[b] + 1;
-    const int nsteps = Tn + Un - 1;
-    const bool multi = blockDim.x > 32;
-    const bool col_ok = u < Un;
-    __shared__ T mailbox[2][32];
-
-    const T* pb = lpb + (long long)b * SK + u;
-    const T* pl = lpl + (long long)b * SK + u;
-    T* po = (is_beta ? betas : alphas) + (long long)b * SK + u;
-
-    T own = neg_inf<T>();   // alpha: alpha(t-1,u)+lpb(t-1,u)   beta: beta(t+1,u)
-    T pass = neg_inf<T>();  // alpha: alpha(t,u)+lpl(t,u)       beta: beta(t,u)   (handed to the neighbour)
-    T result = 0;
-
-    T cb[PF], cl[PF], nb[PF], nl[PF];
-    auto row_of = [&](int i) { return is_beta ? nsteps - 1 - i : i; };  // i-th step -> diagonal
-    auto fetch = [&](int i0, T* vb, T* vl) {
-#pragma unroll
-        for (int j = 0; j < PF; ++j) {
-            const int i = i0 + j;
-            const bool ok = col_ok && i < nsteps;
-            const long long off = (long long)row_of(ok ? i : 0) * maxU;
-            vb[j] = ok ? pb[off] : T(0);
-            vl[j] = ok ? pl[off] : T(0);
-        }
-    };
-    fetch(0, nb, nl);
-    for (int i0 = 0; i0 < nsteps; i0 += PF) {
-#pragma unroll
-        for (int j = 0; j < PF; ++j) { cb[j] = nb[j]; cl[j] = nl[j]; }
-        fetch(i0 + PF, nb, nl);
-#pragma unroll
-        for (int j = 0; j < PF; ++j) {
-            const int i = i0 + j;
-            if (i < nsteps) {  // uniform across the block
-                const int n = row_of(i);
-                const int t = n - u;
-                T nbr = is_beta ? __shfl_down_sync(0xffffffffu, pass, 1) : __shfl_up_sync(0xffffffffu, pass, 1);
-                if (!is_beta && lane == 0) nbr = (warp > 0) ? mailbox[(i & 1) ^ 1][warp - 1] : neg_inf<T>();
-                if (is_beta && lane == 31) nbr = (multi && warp + 1 < (int)(blockDim.x >> 5))
-                                                     ? mailbox[(i & 1) ^ 1][warp + 1] : neg_inf<T>();
-                const bool active = col_ok && t >= 0 && t < Tn;
-                if (active) {
-                    const T vb = cb[j], vl = cl[j];
-                    if (!is_beta) {
-                        // alpha(t,u); own == -inf when t == 0, nbr is unused (forced -inf) when u == 0
-                        const T emit = (u > 0) ? nbr : neg_inf<T>();
-                        const T a = (n == 0) ? T(0) : wave_lse(emit, own);
-                        po[(long long)n * maxU] = a;
-                        own = a + vb;
-                        pass = a + vl;
-                        result = own;  // at the last cell: alpha(T-1,U-1)+lpb(T-1,U-1)
-                    } else {
-                        const T no_emit = (t < Tn - 1) ? own + vb : neg_inf<T>();
-                        const T emit = (u < Un - 1) ? nbr + vl : neg_inf<T>();
-                        const T bt = (t == Tn - 1 && u == Un - 1) ? vb : wave_lse(emit, no_emit);
-                        po[(long long)n * maxU] = bt;
-                        own = bt;
-                        pass = bt;
-                        result = bt;
-                    }
-                }
-                if (multi) {
-                    if (!is_beta && lane == 31) mailbox[i & 1][warp] = pass;
-                    if (is_beta && lane == 0) mailbox[i & 1][warp] = pass;
-                    __syncthreads();
-                }
-            }
-        }
-    }
-    if (!is_beta && u == Un - 1) llf[b] = result;
-    if (is_beta && u == 0) llb[b] = result;
+    if (blockIdx.y == 1) alpha_beta_body<T, PF, true>(lpb, lpl, betas, llb, xlen, ylen, maxU, SK);
+    else alpha_beta_body<T, PF, false>(lpb, lpl, alphas, llf, xlen, ylen, maxU, SK);
 }
 
 // ---------------------------------------------------------------------------------------------
