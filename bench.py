@@ -301,14 +301,16 @@ def main():
     host = {k: (v.pin_memory() if not v.is_pinned() else v) for k, v in host.items()}
     params = [full_dev["W"].clone().requires_grad_(), full_dev["b"].clone().requires_grad_()]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    mode = {"keep": None, "gB": gB}
+    # what a data loader knows on the host: how many 16 x 8 lattice tiles of the batch are valid.  Lets a ragged batch whose
+    # PADDED numerators exceed one workspace chunk (C5) stay one chunk and keep them; ignored for batches that fit anyway (C3)
+    mode = {"keep": None, "gB": gB, "vt": rb.valid_tile_count(host["il"].tolist(), host["ll"].tolist())}
 
     def step(enc, pred, labels, il, ll):
         enc.requires_grad_(), pred.requires_grad_()
         for p in params:
             p.grad = None
         costs = rb.joint_rnnt_loss(enc, pred, params[0], params[1], labels, il, ll, precision=cfg["precision"],
-                                   keep_activations=mode["keep"])
+                                   keep_activations=mode["keep"], valid_tiles=mode["vt"])
         loss_sum = costs.sum()
         (loss_sum / mode["gB"]).backward()                           # run_rnnt.py:278
         ls, dW, db = D.allreduce_loss_and_weight_grads(loss_sum.detach(), params[0].grad, params[1].grad)
@@ -388,6 +390,7 @@ def main():
     if world > 1 and args.scaling == "weak" and B >= world:
         sd, sgB = shard(synth(cfg, 1234, dev), "strong")
         cur["d"], mode["gB"] = sd, sgB
+        mode["vt"] = rb.valid_tile_count(sd["il"].tolist(), sd["ll"].tolist())
         for _ in range(3):
             resident_step()
         ms_s = timed(resident_step, args.steps)

@@ -146,9 +146,15 @@ typedef struct {
     int blank_label;
     int precision; /* rnntb200Precision */
     CUstream stream;
-    /** Reserved (ignored): round 1 let the backward read one int back to compact ragged batches; tiles are now
-     *  ranked on the device and the library never synchronises with the host.  Kept for struct layout stability. */
-    int allow_host_sync;
+    /** 0: unknown.  N > 0: the caller promises that at most N of the batch's 16 x 8 lattice tiles intersect the valid lattice,
+     *  N >= sum_b ceil(T_b / 16) * ceil((U_b + 1) / 8) with U_b = label_lengths[b] (a host-side sum over lengths the data
+     *  loader has anyway).  The kept numerators are indexed by compact tile slots, but only the device knows how many tiles
+     *  are valid (the library never synchronises with the host), so by default the workspace is sized for every tile of
+     *  the padded (maxT, maxU) lattice and a batch whose padded numerators exceed 16 GiB is processed in utterance chunks,
+     *  which rules keep_activations out.  With a bound the workspace holds N row blocks and the batch is one chunk.  If
+     *  the promise is broken nothing is written out of bounds: the forward prints an error and returns NaN costs.
+     *  (Round 1 had `allow_host_sync` here: same offset and type, 0 keeps the old behaviour.) */
+    int valid_tile_bound;
     /** 0: nothing but lse / log-prob pairs / alpha / beta survives the forward; the backward re-runs the projection
      *  chunk by chunk.  1 (tensor-core path): the forward also leaves, in the workspace, the softmax numerators of
      *  every lattice cell as bf16 (2 bytes per logit) and one fp32 reference per lattice row; the backward then skips its own

@@ -10,8 +10,8 @@ Public names follow the reference:
 """
 from .loss import encoder_lengths, get_loss_fn
 from .warprnnt import RNNTLoss, certify_inputs, rnnt_loss, torch_rnnt_loss
-from .joint import Joint, dense1, get_fused_loss_fn, joint_logits, joint_rnnt_loss, joint_step
+from .joint import Joint, dense1, get_fused_loss_fn, joint_logits, joint_rnnt_loss, joint_step, valid_tile_count
 from .train import joint_train_step, make_optimizer
 
 __all__ = ["get_loss_fn", "encoder_lengths", "rnnt_loss", "torch_rnnt_loss", "RNNTLoss", "certify_inputs", "Joint",
-           "joint_rnnt_loss", "joint_logits", "joint_step", "dense1", "get_fused_loss_fn", "joint_train_step", "make_optimizer"]
+           "joint_rnnt_loss", "joint_logits", "joint_step", "dense1", "valid_tile_count", "get_fused_loss_fn", "joint_train_step", "make_optimizer"]

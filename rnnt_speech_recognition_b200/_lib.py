@@ -23,7 +23,7 @@ class JointDesc(C.Structure):
     """rnntb200JointDesc (include/rnnt_b200.h)."""
     _fields_ = [("B", C.c_int), ("maxT", C.c_int), ("maxU", C.c_int), ("H", C.c_int), ("V", C.c_int),
                 ("blank_label", C.c_int), ("precision", C.c_int), ("stream", C.c_void_p),
-                ("allow_host_sync", C.c_int), ("keep_activations", C.c_int)]
+                ("valid_tile_bound", C.c_int), ("keep_activations", C.c_int)]
 
 
 EXPORTS = ("get_warprnnt_version", "rnntGetStatusString", "get_workspace_size", "compute_rnnt_loss",

@@ -305,7 +305,8 @@ __global__ void __launch_bounds__(DZ_THREADS, 1) bwd_dz_kernel(const __grid_cons
                     continue;
                 }
                 const int tile = (bl * p.nTb + tb) * p.nUb + ub;
-                const float rs = __ldg(p.rowscale + (size_t)(p.slot ? p.slot[tile] : tile) * 128 + r);   // 0 outside the lattice
+                const int tslot = p.slot ? p.slot[tile] : tile;              // < 0 only after a broken valid_tile_bound promise
+                const float rs = tslot >= 0 ? __ldg(p.rowscale + (size_t)tslot * 128 + r) : 0.f;   // 0 outside the lattice
 #pragma unroll
                 for (int pass = 0; pass < 2; ++pass) {
                     if (pass >= NP) continue;

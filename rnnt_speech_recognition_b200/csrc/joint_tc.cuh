@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restric
                                                             int b0, int ntiles, int nTb, int nUb, int TT, int UU,
                                                             int* __restrict__ slot, int* __restrict__ count,
                                                             int* __restrict__ tile_of_slot = nullptr,
-                                                            int4* __restrict__ slot_meta = nullptr, int maxT = 0, int maxU = 0) {
+                                                            int4* __restrict__ slot_meta = nullptr, int maxT = 0, int maxU = 0,
+                                                            int max_slots = 0x7fffffff) {
     __shared__ int warp_sums[32];
     __shared__ int base;
     if (threadIdx.x == 0) base = 0;
@@ -202,15 +203,24 @@ __global__ void __launch_bounds__(1024) tile_compact_kernel(const int* __restric
         __syncthreads();
         const int excl = base + warp_sums[warp] + incl - v;
         if (tile < ntiles) {
-            slot[tile] = v ? excl : -1;
-            if (v && tile_of_slot) tile_of_slot[excl] = tile;
-            if (v && slot_meta) slot_meta[excl] = meta;
+            // a valid tile beyond the row blocks the workspace holds (the caller's valid_tile_bound was too small) gets no slot:
+            // nothing is stored for it, the overflow word is raised and the forward call poisons the costs
+            const bool fits = excl < max_slots;
+            slot[tile] = (v && fits) ? excl : -1;
+            if (v && fits && tile_of_slot) tile_of_slot[excl] = tile;
+            if (v && fits && slot_meta) slot_meta[excl] = meta;
         }
         __syncthreads();
         if (threadIdx.x == 1023) base = excl + v;
         __syncthreads();
     }
-    if (threadIdx.x == 0) *count = base;
+    if (threadIdx.x == 0) {
+        count[0] = min(base, max_slots);
+        count[1] = base > max_slots ? base : 0;        // overflow word: the number of valid tiles found
+        if (base > max_slots)
+            printf("rnnt_b200: %d lattice tiles are valid but rnntb200JointDesc.valid_tile_bound promised at most %d -- results are invalid\n",
+                   base, max_slots);
+    }
 }
 // out[i] = sum_k part[k][i] over `nplanes` planes of `n4` float4 each
 __global__ void __launch_bounds__(256) sum_planes_kernel(const float4* __restrict__ part, int nplanes, size_t n4,
@@ -321,6 +331,14 @@ inline TcScratch tc_scratch_layout(const rnntb200JointDesc& d, void* base) {
     if (bc > (size_t)d.B) bc = d.B;
     s.bchunk = (int)bc;
     s.rows_chunk = bc * rows_utt;
+    // The kept arrays are indexed by COMPACT slots (valid tiles only), but how many tiles are valid is known to the device
+    // alone, so the default sizes them for every tile of the padded (maxT, maxU) lattice and chunks the batch.  A caller
+    // that knows its lengths on the host can promise an upper bound: the whole batch is then ONE chunk of that many row
+    // blocks (C5: 46 k valid of 160 k padded tiles -- keep mode instead of 11 recomputing chunks).
+    if (d.valid_tile_bound > 0 && bc < (size_t)d.B) {
+        const size_t tiles = (size_t)d.valid_tile_bound < (size_t)d.B * g.nTb * g.nUb ? (size_t)d.valid_tile_bound : (size_t)d.B * g.nTb * g.nUb;
+        if (tiles * 128 * per_row <= ((size_t)160 << 30)) { bc = d.B; s.bchunk = d.B; s.rows_chunk = tiles * 128; }
+    }
     char* p = static_cast<char*>(base);
     auto take = [&](size_t n) { char* r = p; p += (n + 255) / 256 * 256; return r; };
     s.Wt = reinterpret_cast<__nv_bfloat16*>(take((size_t)d.V * d.H * 2));
@@ -443,7 +461,7 @@ inline rnntStatus_t tc_run_forward(const rnntb200JointDesc& d, const TcGeom& g, 
     if (KEEP) {
         const int ntiles = nb * g.nTb * g.nUb;
         tile_compact_kernel<<<1, 1024, 0, s>>>(xlen, ylen, b0, ntiles, g.nTb, g.nUb, g.TT, g.UU, sc.slot, sc.count, sc.tile_of_slot, sc.slot_meta,
-                                             d.maxT, d.maxU);
+                                             d.maxT, d.maxU, (int)(sc.rows_chunk / 128));
         *launches += 1;
         p.slot = sc.slot; p.dl = sc.dl; p.gm = sc.gm;
     }

@@ -271,7 +271,9 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
         for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = decode_tile(p, tile);
             if (!ti.valid) continue;
-            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
+            const int tslot = p.slot ? p.slot[tile] : tile;                        // row block of this tile in the kept arrays
+            const bool has_slot = tslot >= 0;       // false only when the caller's valid_tile_bound was too small (flagged by tile_compact_kernel)
+            const size_t rowbase = (size_t)(has_slot ? tslot : 0) * 128;
             const int r = warp * 32 + lane;
             const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
             const bool rv = t < ti.Tn && u < ti.Un;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                                     o[i >> 1] = ptx::pack_bf16x2(ptx::ex2_approx(fminf(y[i] - ref, 100.f)), ptx::ex2_approx(fminf(y[i + 1] - ref, 100.f)));
                             }
                         }
-                        if (MODE == 2) {
+                        if (MODE == 2 && has_slot) {
                             __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
                             ptx::st_global_256(dst, o);
                             ptx::st_global_256(dst + 16, o + 8);
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(TC3_THREADS, 1) joint_tc3_kernel(const __grid_
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&acc_empty[buf]);
             }
-            if (MODE == 2) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
+            if (MODE == 2 && has_slot) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
             if (rv && p.lse) {   // (lse == NULL: a backward-time recompute that only wants the kept activations)
                 const float lse2 = m2 + log2f(s);
                 p.lse[cell] = lse2 * LN2;

@@ -317,7 +317,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
                 continue;
             }
             const TileInfo ti = decode_tile(p, tile);
-            const size_t rowbase = (size_t)(p.slot ? p.slot[tile] : tile) * 128;   // row block of this tile in dl / zb
+            const int tslot = p.slot ? p.slot[tile] : tile;                        // row block of this tile in the kept arrays
+            const bool has_slot = tslot >= 0;       // false only when the caller's valid_tile_bound was too small (flagged by tile_compact_kernel)
+            const size_t rowbase = (size_t)(has_slot ? tslot : 0) * 128;
             const int r = warp * 32 + lane;
             const int t = ti.t0 + r / p.UU, u = ti.u0 + r % p.UU;
             const bool rv = t < ti.Tn && u < ti.Un;
@@ -391,7 +393,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
                             s = s * ptx::ex2_approx(m2 - mn) + acc;
                             m2 = mn;
                         }
-                        if (MODE == 2) {
+                        if (MODE == 2 && has_slot) {
                             __nv_bfloat16* dst = p.dl + (rowbase + r) * p.V + col0;
                             ptx::st_global_256(dst, o);
                             ptx::st_global_256(dst + 16, o + 8);
@@ -424,7 +426,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC3_THREADS, 1) join
                 __syncwarp();
                 if (lane == 0) arrive_leader(&acc_empty[buf]);
             }
-            if (MODE == 2) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
+            if (MODE == 2 && has_slot) p.gm[rowbase + r] = ref;   // the row's reference (log2 domain), coalesced
             if (rv && p.lse) {   // (lse == NULL: a backward-time recompute that only wants the kept activations)
                 const float lse2 = m2 + log2f(s);
                 p.lse[cell] = lse2 * LN2;

@@ -49,9 +49,11 @@ struct LossWs {
 // costs[b] = -llForward[b] (cpu_rnnt.h:172), with the reference's consistency guard of the two lattice passes
 // (cpu_rnnt.h:166-170: "WARNING: Forward backward likelihood mismatch" when |llForward - llBackward| > 0.1) as a
 // device-side printf: stream-ordered, costs nothing unless it fires, and needs no read-back.
-__global__ void finish_costs_kernel(const float* __restrict__ llf, const float* __restrict__ llb, float* __restrict__ out, int n) {
+__global__ void finish_costs_kernel(const float* __restrict__ llf, const float* __restrict__ llb, float* __restrict__ out, int n,
+                                    const int* __restrict__ overflow = nullptr) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    if (overflow && *overflow) { out[i] = __int_as_float(0x7fc00000); return; }   // broken valid_tile_bound promise (tile_compact_kernel reported it)
     out[i] = -llf[i];
     const float diff = fabsf(llf[i] - llb[i]);
     if (diff > 0.1f) printf("WARNING: Forward backward likelihood mismatch %f (utterance %d)\n", diff, i);
@@ -382,7 +384,14 @@ rnntStatus_t rnntb200_joint_loss_forward(const rnntb200JointDesc* desc, const fl
     if (st) return st;
     st = launch_alpha_beta(ws.loss, input_lengths, label_lengths, d.B, d.maxT, d.maxU, s);
     if (st) return st;
-    finish_costs_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.loss.llf, ws.loss.llb, costs, d.B);
+    const int* overflow = nullptr;
+#ifndef RNNTB200_NO_TC
+    if (d.precision != RNNTB200_FP32_EXACT) {      // the keeping forward ranked the tiles: its overflow word is fresh
+        const rb::TcScratch sc = rb::tc_scratch_layout(d, ws.scratch);
+        if (rb::tc_keep(d, sc)) overflow = sc.count + 1;
+    }
+#endif
+    finish_costs_kernel<<<(d.B + 127) / 128, 128, 0, s>>>(ws.loss.llf, ws.loss.llb, costs, d.B, overflow);
     RB_LAUNCHED(1);
     return check_launch();
 }

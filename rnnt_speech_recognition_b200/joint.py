@@ -27,10 +27,17 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def _desc(B, T, U, H, V, blank, precision, keep=False):
+def valid_tile_count(input_lengths, label_lengths):
+    """Number of 16 x 8 lattice tiles that intersect the valid lattices of a batch, from HOST copies of the lengths (lists,
+    numpy arrays or CPU tensors): the value `joint_rnnt_loss(..., valid_tiles=...)` / `rnntb200JointDesc.valid_tile_bound`
+    expects.  A data loader has the lengths on the host anyway; the library itself never reads device memory back."""
+    return int(sum(((int(t) + 15) // 16) * ((int(u) + 1 + 7) // 8) for t, u in zip(input_lengths, label_lengths)))
+
+
+def _desc(B, T, U, H, V, blank, precision, keep=False, tile_bound=0):
     # (call inside `with torch.cuda.device(...)`: the stream is the CURRENT stream of the tensors' device)
     return _lib.JointDesc(B, T, U, H, V, int(blank), _PREC[precision],
-                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, 0, 1 if keep else 0)
+                          C.c_void_p(torch.cuda.current_stream().cuda_stream).value, int(tile_bound or 0), 1 if keep else 0)
 
 
 def _workspace(desc, device):
@@ -64,7 +71,7 @@ def _check(enc, pred, W, b, labels, input_lengths, label_lengths):
 
 class _JointRNNT(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision, compact, keep=None):
+    def forward(ctx, enc, pred, W, b, labels, input_lengths, label_lengths, blank, precision, compact, keep=None, valid_tiles=None):
         L = _lib.load()
         enc, pred, W, b = (t.contiguous() for t in (enc, pred, W, b))
         labels, input_lengths, label_lengths = (t.contiguous() for t in (labels, input_lengths, label_lengths))
@@ -75,7 +82,7 @@ class _JointRNNT(torch.autograd.Function):
         with torch.cuda.device(enc.device):
             # a backward will follow: let the forward keep its softmax numerators / tanh outputs in the workspace
             keep = any(ctx.needs_input_grad[:4]) if keep is None else bool(keep)
-            desc = _desc(B, T, U, H, V, blank, precision, keep)
+            desc = _desc(B, T, U, H, V, blank, precision, keep, valid_tiles)
             ws = _workspace(desc, enc.device)
             costs = torch.empty(B, dtype=torch.float32, device=enc.device)
             st = L.rnntb200_joint_loss_forward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
@@ -83,6 +90,7 @@ class _JointRNNT(torch.autograd.Function):
         _lib.check(st, "rnntb200_joint_loss_forward")
         ctx.save_for_backward(enc, pred, W, b, lab, input_lengths, label_lengths)
         ctx.ws, ctx.dims, ctx.blank, ctx.precision, ctx.compact, ctx.keep = ws, (B, T, U, H, V), blank, precision, compact, keep
+        ctx.valid_tiles = valid_tiles
         return costs
 
     @staticmethod
@@ -93,28 +101,31 @@ class _JointRNNT(torch.autograd.Function):
         g = grad_costs.to(torch.float32).contiguous()
         d_enc, d_pred, dW, db = (torch.empty_like(t) for t in (enc, pred, W, b))
         with torch.cuda.device(enc.device):
-            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.keep)
+            desc = _desc(B, T, U, H, V, ctx.blank, ctx.precision, ctx.keep, ctx.valid_tiles)
             st = L.rnntb200_joint_loss_backward(C.byref(desc), _ptr(enc), _ptr(pred), _ptr(W), _ptr(b), _ptr(lab),
                                                 _ptr(label_lengths), _ptr(input_lengths), _ptr(g), _ptr(d_enc),
                                                 _ptr(d_pred), _ptr(dW), _ptr(db), _ptr(ctx.ws))
         _lib.check(st, "rnntb200_joint_loss_backward")
         ctx.ws = None
-        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None
+        return d_enc, d_pred, dW, db, None, None, None, None, None, None, None, None
 
 
 def joint_rnnt_loss(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank=0, precision="bf16",
-                    compact=True, keep_activations=None):
+                    compact=True, keep_activations=None, valid_tiles=None):
     """Per-utterance RNN-T NLL (B,) of logits = tanh(enc_acts[:,:,None]+pred_acts[:,None]) @ W + b,
     differentiable w.r.t. enc_acts, pred_acts, W, b -- without ever materialising (B,T,U,V).
     precision: 'bf16' = the tensor-core path (tcgen05, 16-bit operands, fp32 accumulate) or 'fp32' (exact CUDA-core path).
     compact: accepted for compatibility and ignored -- ragged batches are compacted on the device, the library never
     synchronises with the host.
     keep_activations: None = automatically when a gradient is required (the forward then leaves its softmax
-    numerators (fp16, 2 bytes per logit) in the workspace and the backward is two fused GEMM kernels);
+    numerators (bf16, 2 bytes per logit) in the workspace and the backward is two fused GEMM kernels);
     False = nothing of size O(B*T*U*V) survives the forward call; the backward re-runs the projection chunk by chunk
-    (one more tensor-core pass)."""
+    (one more tensor-core pass).
+    valid_tiles: optional promise `valid_tile_count(host lengths)` (rnntb200JointDesc.valid_tile_bound): sizes the workspace
+    for the batch's valid lattice tiles instead of the padded (T,U) lattice, so that large ragged batches stay one chunk and
+    keep their numerators; a broken promise yields NaN costs and a device-side message, never an out-of-bounds write."""
     return _JointRNNT.apply(enc_acts, pred_acts, W, b, labels, input_lengths, label_lengths, blank, precision, compact,
-                            keep_activations)
+                            keep_activations, valid_tiles)
 
 
 def joint_logits(enc_acts, pred_acts, W, b):

@@ -13,12 +13,12 @@ def dev(a, dtype=None):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()
 
 
-def run_joint(k, precision, scale=None, compact=True, keep=None):
+def run_joint(k, precision, scale=None, compact=True, keep=None, valid_tiles=None):
     import rnnt_speech_recognition_b200 as rb
     t = [dev(k[n], torch.float32).requires_grad_() for n in ("enc", "pred", "W", "b")]
     lab, il, ll = (dev(k[n], torch.int32) for n in ("labels", "input_lengths", "label_lengths"))
     costs = rb.joint_rnnt_loss(*t, lab, il, ll, blank=int(k["blank"]), precision=precision, compact=compact,
-                               keep_activations=keep)
+                               keep_activations=keep, valid_tiles=valid_tiles)
     B = costs.shape[0]
     w = torch.full((B,), 1.0 / B, device="cuda") if scale is None else dev(scale, torch.float32)
     (costs * w).sum().backward()                    # run_rnnt.py:278: sum / global batch

@@ -188,6 +188,31 @@ def test_multi_chunk_backward(tmp_path):
             assert_close(o[n], outs[0][n], rtol=0, atol=0, ntol=2e-5, what=n)
 
 
+def test_valid_tile_bound_keeps_a_multi_chunk_batch_in_one_chunk(tmp_path):
+    """BASELINE C5's situation in miniature: the PADDED numerators of the batch exceed one workspace chunk (forced with
+    RNNTB200_CHUNK_MB=1), so by default the backward recomputes chunk by chunk.  With `valid_tiles` (a host-side count of
+    the lattice tiles that are actually valid) the workspace holds exactly those row blocks, the batch is ONE chunk and the
+    forward keeps its numerators: same costs and gradients, and no recomputing forward launch.  A promise that is too small
+    must not write out of bounds: the costs come back NaN."""
+    args = ["5", "70", "45", "256", "192", "31", "1", "1"]
+    env = dict(os.environ, RNNTB200_CHUNK_MB="1")
+    outs = {}
+    for tag, bound in (("chunked", "0"), ("bound", "1"), ("broken", "3")):
+        f = str(tmp_path / (tag + ".npz"))
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "joint_dump.py"), f] + args + [bound],
+                       check=True, env=env, timeout=300)
+        outs[tag] = dict(np.load(f))
+    kernels = lambda o: " ".join(str(x) for x in o["kernels"])
+    assert "<fwd>" in kernels(outs["chunked"])                      # costs-only forward + recomputing forwards in the backward
+    assert "<fwd>" not in kernels(outs["bound"]) and "<fwd+keep>" in kernels(outs["bound"])
+    assert np.array_equal(outs["bound"]["costs"], outs["chunked"]["costs"])
+    for n in ("d_enc", "d_pred"):
+        assert_close(outs["bound"][n], outs["chunked"][n], rtol=0, atol=0, ntol=1e-6, what=n)
+    for n in ("dW", "db"):
+        assert_close(outs["bound"][n], outs["chunked"][n], rtol=0, atol=0, ntol=2e-5, what=n)
+    assert np.isnan(outs["broken"]["costs"]).all()
+
+
 def test_cuda_graph_capture_and_replay():
     """The whole fused forward + backward is stream-ordered (no host synchronisation, no allocation inside the library
     calls): it can be captured into a CUDA graph and replayed on new input values."""
