@@ -62,3 +62,27 @@ def test_joint_module_parameters_follow_keras_layout():
     assert torch.allclose(got, want, atol=1e-5)
     with pytest.raises((TypeError, OSError, RuntimeError)):
         j.hoist(f, g)
+
+
+def test_valid_tile_count_and_the_workspace_it_buys():
+    """`valid_tile_count` is the host-side sum the descriptor's `valid_tile_bound` expects, and the workspace size is a pure
+    function of the descriptor (no GPU needed): for BASELINE C5's shape the padded numerators need several chunks of 16 GiB,
+    the promise of the valid tiles turns that into one chunk sized for them."""
+    import ctypes as C
+    from rnnt_speech_recognition_b200 import _lib
+    assert rb.valid_tile_count([16, 17, 1], [7, 8, 0]) == 1 * 1 + 2 * 2 + 1 * 1       # ceil(T/16) * ceil((U+1)/8)
+    L = _lib.load(build_if_missing=True)
+    B, T, U, V, H = 64, 1600, 200, 4096, 640
+    rng = np.random.default_rng(0)
+    il, ll = rng.integers(100, T + 1, B), rng.integers(10, U + 1, B) - 1
+    vt = rb.valid_tile_count(il, ll)
+    sizes = []
+    for bound in (0, vt):
+        d = _lib.JointDesc(B, T, U, H, V, 0, 1, None, bound, 1)
+        s = C.c_size_t(0)
+        assert L.rnntb200_joint_workspace_size(C.byref(d), C.byref(s)) == 0
+        sizes.append(s.value)
+    per_row = V * 2 + 8
+    assert sizes[0] < 40 << 30                                    # padded: chunks of <= 16 GiB of numerators (+ planes)
+    assert sizes[1] >= vt * 128 * per_row                         # one chunk that holds every valid row block
+    assert sizes[1] < 64 * ((T + 15) // 16) * ((U + 7) // 8) * 128 * per_row / 2     # far below the padded lattice
