@@ -213,6 +213,24 @@ def test_valid_tile_bound_keeps_a_multi_chunk_batch_in_one_chunk(tmp_path):
     assert np.isnan(outs["broken"]["costs"]).all()
 
 
+def test_one_cta_kernel_forms_agree_with_the_pair_kernels(tmp_path):
+    """The one-CTA forms of the three tensor-core kernels (RNNTB200_FWD=3, RNNTB200_DZ=1, RNNTB200_DW=1: A/B references of the
+    CTA-pair kernels, selected once per process) compute the same function: costs to 1e-5 relative, gradients to the
+    16-bit path's own noise level (summation orders differ)."""
+    args = ["3", "40", "21", "576", "640", "17", "1", "1"]       # ragged, two dZ passes, two v-tiles (512 + 64), odd u-block counts
+    outs = {}
+    for tag, env in (("pair", {}), ("one", {"RNNTB200_FWD": "3", "RNNTB200_DZ": "1", "RNNTB200_DW": "1"})):
+        f = str(tmp_path / (tag + ".npz"))
+        subprocess.run([sys.executable, os.path.join(ROOT, "tools", "joint_dump.py"), f] + args,
+                       check=True, env=dict(os.environ, **env), timeout=300)
+        outs[tag] = dict(np.load(f))
+    k = " ".join(str(x) for x in outs["one"]["kernels"])
+    assert "joint_tc3_kernel" in k and "bwd_dw_kernel" in k and "bwd_dw2_kernel" not in k
+    assert_close(outs["one"]["costs"], outs["pair"]["costs"], rtol=1e-5, atol=1e-4, what="costs")
+    for n in NAMES:
+        assert_close(outs["one"][n], outs["pair"][n], rtol=0, atol=0, ntol=2e-3, what=n)
+
+
 def test_cuda_graph_capture_and_replay():
     """The whole fused forward + backward is stream-ordered (no host synchronisation, no allocation inside the library
     calls): it can be captured into a CUDA graph and replayed on new input values."""
