@@ -1,9 +1,9 @@
-"""Bring-up check of the own-kernel backward (csrc/bwd_tc.cuh): runs a list of shapes through joint_rnnt_loss on the
-tensor-core path and compares every gradient with the fp32 exact CUDA path of the same library (and, with --ab, with
-another backward implementation selected by RNNTB200_BWD in a child process).
+"""Bring-up check of the tensor-core path (csrc/joint_tc4.cuh, bwd_tc.cuh): runs a list of shapes through joint_rnnt_loss in
+keep and in recompute mode and compares costs and every gradient with the fp32 exact CUDA path of the same library, and the
+two modes with each other (they must agree bit for bit).  Quicker than the pytest suite while a kernel is being changed;
+combine with RNNTB200_FWD / RNNTB200_DZ / RNNTB200_DW to check the one-CTA forms.
 
-    timeout 600 python tools/bwd_check.py            # own kernels vs fp32 exact path
-    timeout 600 python tools/bwd_check.py --dump f   # (used by --ab)
+    timeout 600 python tools/bwd_check.py
 """
 import os
 import subprocess
