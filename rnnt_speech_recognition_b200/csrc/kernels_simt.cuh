@@ -262,7 +262,9 @@ __device__ __forceinline__ void alpha_beta_body(const T* __restrict__ lpb, const
 
     const int lag = (multi && warp < nwarps) ? (BETA ? nwarps - 1 - warp : warp) * PF : 0;   // this warp runs `lag` steps behind the first one
     const int src = BETA ? warp + 1 : warp - 1;                                  // neighbour warp whose edge lane feeds this one
-    const bool has_src = BETA ? (warp + 1 < nwarps) : (warp > 0);
+    // (warps beyond the utterance's last column own nothing, run un-skewed and must not touch the ring: their reads would
+    //  race with the working warps' writes of the same macro iteration)
+    const bool has_src = BETA ? (warp + 1 < nwarps) : (warp > 0 && warp < nwarps);
     const bool edge_in = lane == (BETA ? 31 : 0), edge_out = multi && lane == (BETA ? 0 : 31);
     const int nmacro = (nsteps + PF - 1) / PF + (multi ? nwarps - 1 : 0);
     // step i works on diagonal n = i (alpha) / nsteps - 1 - i (beta): row n of the skewed planes, one pointer bump per step
@@ -311,7 +313,7 @@ __device__ __forceinline__ void alpha_beta_body(const T* __restrict__ lpb, const
                     pass = BETA ? val : val + vl;
                     result = own;      // alpha, last cell: alpha(T-1,U-1)+lpb(T-1,U-1);  beta, cell (0,0): beta(0,0)
                 }
-                if (edge_out) mailbox[warp][i & (RING - 1)] = pass;
+                if (edge_out && warp < nwarps) mailbox[warp][i & (RING - 1)] = pass;
             }
         }
         if (multi) __syncthreads();
